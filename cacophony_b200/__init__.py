@@ -1,0 +1,14 @@
+"""cacophony_b200 — B200-native (sm_100a) implementation of Cacophony's inference hot path.
+
+Mirrors the export list of the reference's ``src/caco_torch/__init__.py`` plus the frontend functions of
+``src/eval/eval_caco_torch.py``; all arithmetic runs in ``libcaco_b200.so`` (C ABI: ``include/caco_b200.h``).
+"""
+from .model import (CACO, CACOConfig, AudioAttentionPooler, create_caco_model, AudioEncoder, AudioTransformerConfig,
+                    RobertaModel, RobertaConfig, NORM_EPS)
+from .frontend import DatasetConfig, compute_mel_spectrogram, spectrogram_to_patches, prepare_audio_batch
+
+__all__ = [
+    "CACO", "CACOConfig", "AudioAttentionPooler", "create_caco_model", "AudioEncoder", "AudioTransformerConfig",
+    "RobertaModel", "RobertaConfig", "NORM_EPS", "DatasetConfig", "compute_mel_spectrogram", "spectrogram_to_patches",
+    "prepare_audio_batch",
+]

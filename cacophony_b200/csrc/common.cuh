@@ -1,0 +1,41 @@
+// Shared host-side helpers for the library's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+namespace caco {
+
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms();
+
+// op-level entry points implemented across the .cu files (C++ side of the C ABI)
+int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
+             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream);
+int frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
+             float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream);
+int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
+              int dim, cudaStream_t stream);
+int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
+                  int dim, cudaStream_t stream);
+int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
+                    cudaStream_t stream);
+int attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
+                   cudaStream_t stream);
+int text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
+                  const float* type0, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
+                  int batch, int T, int dim, int vocab, int max_pos, cudaStream_t stream);
+int attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
+              const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads, int dim,
+              cudaStream_t stream);
+int sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha, float* out, int ldo,
+             int M, int N, int K, cudaStream_t stream);
+int l2norm(const float* in, float* out, int rows, int dim, float eps, cudaStream_t stream);
+int sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt, int dim,
+               cudaStream_t stream);
+
+}  // namespace caco

@@ -1,0 +1,398 @@
+// Model handle: the C++ side of CACO (src/caco_torch/caco.py:82-261).  Owns fp16-packed GEMM weights, the folded
+// pooler vectors and an activation workspace; borrows everything else (biases, LayerNorm parameters, embedding
+// tables, inputs, outputs) from the caller.  The two towers are straight-line sequences of the kernels in
+// gemm.cu / attention.cu / rowops.cu on ONE stream — at batch 256 every launch is milliseconds long, so there is
+// nothing for a graph to save; the host cost is ~100 launches per tower.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "caco_b200.h"
+#include "common.cuh"
+
+namespace caco {
+int fold_query(const float* query, const float* wk, const float* bk, float qscale, float* u, float* c, int heads, int dh,
+               int dim, cudaStream_t stream);
+static thread_local char g_err[256] = "";
+static void set_err(const char* fmt, const char* a) { snprintf(g_err, sizeof(g_err), fmt, a); }
+}  // namespace caco
+
+struct caco_model {
+  caco_config cfg;
+  struct T { const float* p; int64_t n; };
+  std::unordered_map<std::string, T> w;
+  bool packed = false;
+
+  struct ALayer {
+    const __half *qkv_w, *out_w, *fc1_w, *fc2_w;
+    const float *qkv_b, *out_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  };
+  struct TLayer {
+    const __half *qkv_w, *o_w, *fc1_w, *fc2_w;
+    const float *qkv_b, *o_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  };
+  std::vector<ALayer> al;
+  std::vector<TLayer> tl;
+  const __half* in_w = nullptr;
+  const float *in_b = nullptr, *freq_emb = nullptr, *an_g = nullptr, *an_b = nullptr;
+  const float *ap_vw = nullptr, *ap_vb = nullptr, *ap_ow = nullptr, *ap_ob = nullptr;   // audio pooler value rows / out_proj
+  const float *word = nullptr, *pos = nullptr, *type0 = nullptr, *te_g = nullptr, *te_b = nullptr;
+  const float *tp_vw = nullptr, *tp_vb = nullptr, *proj_w = nullptr, *proj_b = nullptr;
+  const float* logit_scale = nullptr;
+
+  __half* arena16 = nullptr;   // all fp16 GEMM weights
+  float* arena32 = nullptr;    // packed text qkv biases + folded pooler vectors
+  float *a_u = nullptr, *a_c = nullptr, *t_u = nullptr, *t_c = nullptr;
+
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace caco {
+
+static const float* need(caco_model* m, const std::string& key, int64_t numel, int* rc) {
+  auto it = m->w.find(key);
+  if (it == m->w.end()) { set_err("missing tensor %s", key.c_str()); *rc = CACO_ERR_STATE; return nullptr; }
+  if (it->second.n != numel) { set_err("wrong size for %s", key.c_str()); *rc = CACO_ERR_STATE; return nullptr; }
+  return it->second.p;
+}
+
+static int ensure_ws(caco_model* m, size_t bytes) {
+  if (bytes <= m->ws_bytes) return 0;
+  if (m->ws) { cudaDeviceSynchronize(); cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; }
+  cudaError_t e = cudaMalloc(&m->ws, bytes);
+  if (e != cudaSuccess) return (int)e;
+  m->ws_bytes = bytes;
+  return 0;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+#define CK(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+static int pack(caco_model* m, cudaStream_t st) {
+  const caco_config& c = m->cfg;
+  const int64_t D = c.hidden, F = c.ffn, P = c.patch_dim;
+  int rc = 0;
+  // ---- sizes
+  const int64_t per_layer = 3 * D * D + D * D + 2 * F * D;
+  const int64_t n16 = P * D + per_layer * (c.audio_layers + c.text_layers);
+  const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * (D + 1) + 64;
+  if (m->arena16) cudaFree(m->arena16);
+  if (m->arena32) cudaFree(m->arena32);
+  cudaError_t e = cudaMalloc(&m->arena16, n16 * sizeof(__half));
+  if (e) return (int)e;
+  e = cudaMalloc(&m->arena32, n32 * sizeof(float));
+  if (e) return (int)e;
+  __half* p16 = m->arena16;
+  float* p32 = m->arena32;
+  auto take16 = [&](const float* src, int64_t n) -> const __half* {
+    __half* dst = p16;
+    p16 += n;
+    if (src && rc == 0) rc = cast_f32_f16(src, dst, n, st);
+    return dst;
+  };
+  // ---- audio tower (key names: SURVEY.md §8b)
+  const std::string A = "audio_module.";
+  m->in_w = take16(need(m, A + "input_proj.weight", D * P, &rc), D * P);
+  m->in_b = need(m, A + "input_proj.bias", D, &rc);
+  m->freq_emb = need(m, A + "freq_positional_embedding", (int64_t)c.n_freq * D, &rc);
+  m->an_g = need(m, A + "norm.weight", D, &rc);
+  m->an_b = need(m, A + "norm.bias", D, &rc);
+  m->al.resize(c.audio_layers);
+  for (int i = 0; i < c.audio_layers && rc == 0; ++i) {
+    const std::string L = A + "layers." + std::to_string(i) + ".";
+    caco_model::ALayer& l = m->al[i];
+    l.ln1_g = need(m, L + "norm1.weight", D, &rc);
+    l.ln1_b = need(m, L + "norm1.bias", D, &rc);
+    l.ln2_g = need(m, L + "norm2.weight", D, &rc);
+    l.ln2_b = need(m, L + "norm2.bias", D, &rc);
+    l.qkv_w = take16(need(m, L + "attn.in_proj_weight", 3 * D * D, &rc), 3 * D * D);
+    l.qkv_b = need(m, L + "attn.in_proj_bias", 3 * D, &rc);
+    l.out_w = take16(need(m, L + "attn.out_proj.weight", D * D, &rc), D * D);
+    l.out_b = need(m, L + "attn.out_proj.bias", D, &rc);
+    l.fc1_w = take16(need(m, L + "mlp.fc1.weight", F * D, &rc), F * D);
+    l.fc1_b = need(m, L + "mlp.fc1.bias", F, &rc);
+    l.fc2_w = take16(need(m, L + "mlp.fc2.weight", D * F, &rc), D * F);
+    l.fc2_b = need(m, L + "mlp.fc2.bias", D, &rc);
+  }
+  if (rc) return rc;
+  // ---- audio pooler (caco.py:24-79): fold kv_proj's key half into the query
+  {
+    const std::string Q = "audio_attention_pool.";
+    const float* query = need(m, Q + "query", D, &rc);
+    const float* kvw = need(m, Q + "kv_proj.weight", 2 * D * D, &rc);
+    const float* kvb = need(m, Q + "kv_proj.bias", 2 * D, &rc);
+    m->ap_ow = need(m, Q + "out_proj.weight", D * D, &rc);
+    m->ap_ob = need(m, Q + "out_proj.bias", D, &rc);
+    if (rc) return rc;
+    m->ap_vw = kvw + D * D;
+    m->ap_vb = kvb + D;
+    m->a_u = p32; p32 += (int64_t)c.pool_heads * D;
+    m->a_c = p32; p32 += c.pool_heads;
+    const int dh = (int)D / c.pool_heads;
+    CK(fold_query(query, kvw, kvb, 1.0f / sqrtf((float)dh), m->a_u, m->a_c, c.pool_heads, dh, (int)D, st));
+  }
+  // ---- text tower
+  const std::string Tm = "text_module.";
+  m->word = need(m, Tm + "embeddings.word_embeddings.weight", (int64_t)c.vocab * D, &rc);
+  m->pos = need(m, Tm + "embeddings.position_embeddings.weight", (int64_t)c.max_pos * D, &rc);
+  m->type0 = need(m, Tm + "embeddings.token_type_embeddings.weight", D, &rc);
+  m->te_g = need(m, Tm + "embeddings.LayerNorm.weight", D, &rc);
+  m->te_b = need(m, Tm + "embeddings.LayerNorm.bias", D, &rc);
+  m->tl.resize(c.text_layers);
+  for (int i = 0; i < c.text_layers && rc == 0; ++i) {
+    const std::string L = Tm + "encoder.layers." + std::to_string(i) + ".";
+    caco_model::TLayer& l = m->tl[i];
+    // q | k | v stacked into one [3D, D] weight so the three projections are one GEMM (roberta.py:77-83)
+    __half* qkv = p16;
+    float* qkvb = p32;
+    const char* nm[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      take16(need(m, L + "attention.self." + nm[j] + ".weight", D * D, &rc), D * D);
+      const float* b = need(m, L + "attention.self." + nm[j] + ".bias", D, &rc);
+      if (rc) return rc;
+      e = cudaMemcpyAsync(p32, b, D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      if (e) return (int)e;
+      p32 += D;
+    }
+    l.qkv_w = qkv;
+    l.qkv_b = qkvb;
+    l.o_w = take16(need(m, L + "attention.output.dense.weight", D * D, &rc), D * D);
+    l.o_b = need(m, L + "attention.output.dense.bias", D, &rc);
+    l.ln1_g = need(m, L + "attention.output.LayerNorm.weight", D, &rc);
+    l.ln1_b = need(m, L + "attention.output.LayerNorm.bias", D, &rc);
+    l.fc1_w = take16(need(m, L + "intermediate.dense.weight", F * D, &rc), F * D);
+    l.fc1_b = need(m, L + "intermediate.dense.bias", F, &rc);
+    l.fc2_w = take16(need(m, L + "output.dense.weight", D * F, &rc), D * F);
+    l.fc2_b = need(m, L + "output.dense.bias", D, &rc);
+    l.ln2_g = need(m, L + "output.LayerNorm.weight", D, &rc);
+    l.ln2_b = need(m, L + "output.LayerNorm.bias", D, &rc);
+  }
+  if (rc) return rc;
+  {
+    const std::string Q = Tm + "pooler.";
+    const float* query = need(m, Q + "attention_pool_query", D, &rc);
+    const float* kw = need(m, Q + "key_proj.weight", D * D, &rc);
+    const float* kb = need(m, Q + "key_proj.bias", D, &rc);
+    m->tp_vw = need(m, Q + "value_proj.weight", D * D, &rc);
+    m->tp_vb = need(m, Q + "value_proj.bias", D, &rc);
+    m->proj_w = need(m, "text_proj.weight", D * D, &rc);
+    m->proj_b = need(m, "text_proj.bias", D, &rc);
+    m->logit_scale = need(m, "logit_scale", 1, &rc);
+    if (rc) return rc;
+    m->t_u = p32; p32 += D;
+    m->t_c = p32; p32 += 1;
+    CK(fold_query(query, kw, kb, 1.0f / sqrtf((float)D), m->t_u, m->t_c, 1, (int)D, (int)D, st));   // roberta.py:259
+  }
+  m->packed = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- audio tower
+static int audio_chunk(caco_model* m, const float* patches, const float* t_inds, const float* f_inds, const float* mask,
+                       int B, int S, int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
+  const caco_config& c = m->cfg;
+  const int D = c.hidden, F = c.ffn, P = c.patch_dim;
+  const size_t R = (size_t)B * S;
+  // workspace carve-up
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const size_t o_x = carve(R * D * 4), o_h = carve(R * D * 2), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2);
+  const size_t o_mlp = carve(R * (size_t)F * 2), o_p16 = carve(R * P * 2);
+  const size_t o_pool = carve((size_t)B * c.pool_heads * D * 4), o_o = carve((size_t)B * D * 4), o_e = carve((size_t)B * D * 4);
+  CK(ensure_ws(m, off));
+  uint8_t* w = (uint8_t*)m->ws;
+  float* x = (float*)(w + o_x);
+  __half* h16 = (__half*)(w + o_h);
+  __half* qkv = (__half*)(w + o_qkv);
+  __half* att = (__half*)(w + o_att);
+  __half* mlp = (__half*)(w + o_mlp);
+  __half* p16 = (__half*)(w + o_p16);
+  float* pooled = (float*)(w + o_pool);
+  float* ov = (float*)(w + o_o);
+  float* eraw = (float*)(w + o_e);
+  const int Ri = (int)R;
+
+  // input projection + position embeddings (mae.py:133-142)
+  CK(cast_f32_f16(patches, p16, (int64_t)R * P, st));
+  CK(gemm_f16(p16, P, m->in_w, P, m->in_b, nullptr, 0, x, D, Ri, D, P, CACO_EPI_BIAS_F32, 0, 0, st));
+  CK(audio_add_pos(x, t_inds, f_inds, m->freq_emb, c.n_freq, Ri, D, st));
+  // pre-LN blocks (mae.py:80-99)
+  for (int i = 0; i < c.audio_layers; ++i) {
+    const caco_model::ALayer& l = m->al[i];
+    CK(layernorm(x, l.ln1_g, l.ln1_b, c.ln_eps, nullptr, h16, Ri, D, st));
+    CK(gemm_f16(h16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, D, CACO_EPI_BIAS_F16, 0, 0, st));
+    CK(attention_audio(qkv, mask, att, B, S, c.audio_heads, D / c.audio_heads, st));
+    CK(gemm_f16(att, D, l.out_w, D, l.out_b, x, D, x, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+    CK(layernorm(x, l.ln2_g, l.ln2_b, c.ln_eps, nullptr, h16, Ri, D, st));
+    CK(gemm_f16(h16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, D, CACO_EPI_BIAS_SILU_F16, 0, 0, st));
+    CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, x, D, x, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+  }
+  // final LN (mae.py:147) fused into the pooler's pass over the rows (caco.py:41-79)
+  CK(attn_pool(x, mask, m->a_u, m->a_c, m->an_g, m->an_b, c.ln_eps, hidden_out, pooled, B, S, c.pool_heads, D, st));
+  const int dh = D / c.pool_heads;
+  for (int h = 0; h < c.pool_heads; ++h)
+    CK(sgemm_nt(pooled + (size_t)h * D, c.pool_heads * D, m->ap_vw + (size_t)h * dh * D, D, m->ap_vb + h * dh, 1.0f,
+                ov + h * dh, D, B, dh, D, st));
+  float* dst = normalize ? eraw : emb_out;
+  CK(sgemm_nt(ov, D, m->ap_ow, D, m->ap_ob, 1.0f, dst, D, B, D, D, st));
+  if (normalize) CK(l2norm(eraw, emb_out, B, D, 1e-10f, st));
+  return 0;
+}
+
+static int audio_embedding(caco_model* m, const float* patches, const float* t_inds, const float* f_inds, const float* mask,
+                           int B, int S, int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
+  if (!m || !m->packed) return CACO_ERR_STATE;
+  if (!patches || !t_inds || !f_inds || !mask || !emb_out || B <= 0 || S <= 0) return CACO_ERR_ARG;
+  const caco_config& c = m->cfg;
+  // bound the workspace: at most ~131072 token rows per pass (256 clips of 500 tokens)
+  int chunk = (int)(131072 / S);
+  if (chunk < 1) chunk = 1;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    const size_t r0 = (size_t)b0 * S;
+    CK(audio_chunk(m, patches + r0 * c.patch_dim, t_inds + r0, f_inds + r0, mask + r0, nb, S, normalize,
+                   emb_out + (size_t)b0 * c.hidden, hidden_out ? hidden_out + r0 * c.hidden : nullptr, st));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- text tower
+static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, const int64_t* pids, int B, int T,
+                          int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
+  if (!m || !m->packed) return CACO_ERR_STATE;
+  if (!ids || !mask || !emb_out || B <= 0 || T <= 0) return CACO_ERR_ARG;
+  const caco_config& c = m->cfg;
+  const int D = c.hidden, F = c.ffn;
+  int chunk = 131072 / T;
+  if (chunk < 1) chunk = 1;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    const size_t R = (size_t)nb * T;
+    const int Ri = (int)R;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+    const size_t o_x = carve(R * D * 4), o_x16 = carve(R * D * 2), o_a = carve(R * D * 4), o_a16 = carve(R * D * 2);
+    const size_t o_tmp = carve(R * D * 4), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2);
+    const size_t o_pool = carve((size_t)nb * D * 4), o_v = carve((size_t)nb * D * 4), o_e = carve((size_t)nb * D * 4);
+    CK(ensure_ws(m, off));
+    uint8_t* w = (uint8_t*)m->ws;
+    float* x = (float*)(w + o_x);
+    __half* x16 = (__half*)(w + o_x16);
+    float* a = (float*)(w + o_a);
+    __half* a16 = (__half*)(w + o_a16);
+    float* tmp = (float*)(w + o_tmp);
+    __half* qkv = (__half*)(w + o_qkv);
+    __half* att = (__half*)(w + o_att);
+    __half* mlp = (__half*)(w + o_mlp);
+    float* pooled = (float*)(w + o_pool);
+    float* val = (float*)(w + o_v);
+    float* eraw = (float*)(w + o_e);
+    const int64_t* ids_c = ids + (size_t)b0 * T;
+    const int64_t* pids_c = pids ? pids + (size_t)b0 * T : nullptr;
+    const float* mask_c = mask + (size_t)b0 * T;
+
+    CK(text_embed_ln(ids_c, pids_c, m->word, m->pos, m->type0, m->te_g, m->te_b, c.ln_eps, x, x16, nb, T, D, c.vocab,
+                     c.max_pos, st));
+    for (int i = 0; i < c.text_layers; ++i) {   // post-LN blocks (roberta.py:191-215)
+      const caco_model::TLayer& l = m->tl[i];
+      CK(gemm_f16(x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, D, CACO_EPI_BIAS_F16, 0, 0, st));
+      CK(attention_text(qkv, mask_c, att, nb, T, c.text_heads, D / c.text_heads, st));
+      CK(gemm_f16(att, D, l.o_w, D, l.o_b, x, D, tmp, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(layernorm(tmp, l.ln1_g, l.ln1_b, c.ln_eps, a, a16, Ri, D, st));
+      CK(gemm_f16(a16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, D, CACO_EPI_BIAS_GELU_F16, 0, 0, st));
+      CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, a, D, tmp, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(layernorm(tmp, l.ln2_g, l.ln2_b, c.ln_eps, x, x16, Ri, D, st));
+    }
+    if (hidden_out) {
+      cudaError_t e = cudaMemcpyAsync(hidden_out + (size_t)b0 * T * D, x, R * D * 4, cudaMemcpyDeviceToDevice, st);
+      if (e) return (int)e;
+    }
+    CK(attn_pool(x, mask_c, m->t_u, m->t_c, nullptr, nullptr, 0.f, nullptr, pooled, nb, T, 1, D, st));   // roberta.py:253-271
+    CK(sgemm_nt(pooled, D, m->tp_vw, D, m->tp_vb, 1.0f, val, D, nb, D, D, st));
+    float* dst = normalize ? eraw : emb_out + (size_t)b0 * D;
+    CK(sgemm_nt(val, D, m->proj_w, D, m->proj_b, 1.0f, dst, D, nb, D, D, st));                            // caco.py:169
+    if (normalize) CK(l2norm(eraw, emb_out + (size_t)b0 * D, nb, D, 1e-10f, st));
+  }
+  return 0;
+}
+
+}  // namespace caco
+
+extern "C" {
+
+const char* caco_last_error(void) { return caco::g_err; }
+
+int caco_model_create(const caco_config* cfg, caco_model** out) {
+  if (!cfg || !out) return CACO_ERR_ARG;
+  if (cfg->hidden % 128 || cfg->hidden > 1024 || cfg->hidden % cfg->audio_heads || cfg->hidden % cfg->text_heads ||
+      cfg->hidden % cfg->pool_heads || cfg->pool_heads > 4)
+    return CACO_ERR_ARG;
+  const int adh = cfg->hidden / cfg->audio_heads;
+  if ((adh != 96 && adh != 64) || cfg->hidden / cfg->text_heads != 64) return CACO_ERR_ARG;
+  caco_model* m = new caco_model();
+  m->cfg = *cfg;
+  *out = m;
+  return 0;
+}
+
+void caco_model_destroy(caco_model* m) {
+  if (!m) return;
+  cudaDeviceSynchronize();
+  if (m->arena16) cudaFree(m->arena16);
+  if (m->arena32) cudaFree(m->arena32);
+  if (m->ws) cudaFree(m->ws);
+  delete m;
+}
+
+int caco_model_set_tensor(caco_model* m, const char* key, const float* dev_ptr, int64_t numel) {
+  if (!m || !key || !dev_ptr || numel <= 0) return CACO_ERR_ARG;
+  if (strncmp(key, "decoder_module.", 15) == 0) return 1;   // captioning head: not on this path
+  m->w[key] = caco_model::T{dev_ptr, numel};
+  m->packed = false;
+  return 0;
+}
+
+int caco_model_pack(caco_model* m, void* stream) {
+  if (!m) return CACO_ERR_ARG;
+  return caco::pack(m, (cudaStream_t)stream);
+}
+
+int caco_model_audio_embedding(caco_model* m, const float* patches, const float* time_inds, const float* freq_inds,
+                               const float* mask, int batch, int seq, int normalize, float* emb_out, float* hidden_out,
+                               void* stream) {
+  return caco::audio_embedding(m, patches, time_inds, freq_inds, mask, batch, seq, normalize, emb_out, hidden_out,
+                               (cudaStream_t)stream);
+}
+
+int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* mask, const int64_t* position_ids, int batch,
+                              int T, int normalize, float* emb_out, float* hidden_out, void* stream) {
+  return caco::text_embedding(m, ids, mask, position_ids, batch, T, normalize, emb_out, hidden_out, (cudaStream_t)stream);
+}
+
+int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
+                            float* emb_out, void* stream) {
+  if (!m || !m->packed) return CACO_ERR_STATE;
+  if (!wave || !emb_out || batch <= 0) return CACO_ERR_ARG;
+  // frontend outputs live in a side allocation so the tower's workspace carve-up stays independent
+  const size_t R = (size_t)batch * max_patches;
+  float* buf = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&buf, (R * 256 + 3 * R) * sizeof(float), (cudaStream_t)stream);
+  if (e) return (int)e;
+  float *patches = buf, *ti = buf + R * 256, *fi = ti + R, *mk = fi + R;
+  int rc = caco::frontend(wave, batch, n_samples, max_patches, patches, nullptr, ti, fi, mk, nullptr, (cudaStream_t)stream);
+  if (!rc) rc = caco::audio_embedding(m, patches, ti, fi, mk, batch, max_patches, normalize, emb_out, nullptr, (cudaStream_t)stream);
+  cudaFreeAsync(buf, (cudaStream_t)stream);
+  return rc;
+}
+
+const float* caco_model_logit_scale(caco_model* m) { return m ? m->logit_scale : nullptr; }
+}

@@ -1,0 +1,380 @@
+// K2 — dense contraction for every nn.Linear on the path (SURVEY.md §2 "K2 gemm_bias_act"):
+//   out[M,N] = epilogue( A[M,K] (fp16, row-major) · W[N,K]^T (fp16, row-major = nn.Linear.weight) )
+// replacing mae.py:51-52,116 / MHA in/out-proj mae.py:69 / roberta.py:62-64,110,153,164 / caco.py:35,37.
+//
+// sm_100a design: persistent, warp-specialised.  warp 0 = TMA producer (SWIZZLE_128B tiles of
+// 128 x 64 fp16 into a STAGES-deep smem ring), warp 1 = tcgen05.mma issuer (fp32 accumulators in
+// tensor memory, two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1),
+// warps 2.. = epilogue (tcgen05.ld -> per-warp smem transpose -> coalesced 128-bit global I/O with
+// fused bias / SiLU / erf-GELU / fp32 residual add / fp16 or fp32 store).
+// CG = 2 runs a CTA pair (cluster of 2) on one 256 x BN tile with cta_group::2 MMAs: each CTA
+// stages its own 128 rows of A and half of the W tile, which halves the smem/L2 operand traffic
+// per FLOP (the limiter on B200: L2->SM bandwidth, not the tensor pipe).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "caco_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace caco {
+
+constexpr int BM = 128;   // rows per CTA
+constexpr int BK = 64;    // fp16 elements per 128-byte swizzle row
+constexpr int UK = 16;    // K per tcgen05.mma (kind::f16)
+constexpr int EPI_COLS = 32;
+constexpr int STG_LD = 36;  // fp32 words per staged row (32 + 4 pad: conflict-free 128-bit access)
+
+struct GemmArgs {
+  int M, N, K;
+  int ldo, ldr;
+  const float* bias;
+  const float* resid;
+  void* out;
+  int num_m_blocks;  // in units of BM*CG rows
+  int num_n_blocks;
+};
+
+template <int CG, int BN, int STAGES, int EPI_WARPS>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = 32 * (2 + EPI_WARPS);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "tmem columns must be a power of two");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>
+__global__ void __launch_bounds__(GemmCfg<CG, BN, STAGES, EPI_WARPS>::THREADS, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+  using Cfg = GemmCfg<CG, BN, STAGES, EPI_WARPS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  float* stg_all = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
+  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES;
+  const uint32_t bar_full = bars;                       // STAGES x 8 B
+  const uint32_t bar_empty = bars + 8 * STAGES;         // STAGES x 8 B
+  const uint32_t bar_tfull = bars + 16 * STAGES;        // 2 x 8 B
+  const uint32_t bar_tempty = bars + 16 * STAGES + 16;  // 2 x 8 B
+  const uint32_t tmem_slot = bars + 16 * STAGES + 32;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 16 * STAGES + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, CG);   // one arrive per producing CTA (+ tx bytes)
+      mbar_init(bar_empty + 8 * s, 1);   // one tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);                   // one tcgen05.commit
+      mbar_init(bar_tempty + 8 * s, CG * EPI_WARPS);     // every epilogue warp of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (lane 0 issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int mb = tile / g.num_n_blocks, nb = tile % g.num_n_blocks;
+      const int row_a = (mb * CG + (int)cta_rank) * BM;
+      const int row_b = nb * BN + (int)cta_rank * Cfg::B_ROWS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t full = bar_full + 8 * stage;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(full, Cfg::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
+          } else {
+            // both CTAs register their bytes on the LEADER's barrier
+            if (leader) mbar_expect_tx(full, Cfg::STAGE_BYTES);
+            else asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(mapa(full, 0)), "r"((uint32_t)Cfg::STAGE_BYTES) : "memory");
+            tma_load_2d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
+            tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only, lane 0 issues)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * CG, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(smem_a + stage * Cfg::A_BYTES);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              // +32 bytes per K step inside the 128-byte swizzle row -> +2 in the 16-byte address field
+              umma_f16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CG == 1) {
+              umma_commit<1>(bar_empty + 8 * stage);
+              if (kb == num_kb - 1) umma_commit<1>(bar_tfull + 8 * acc);
+            } else {
+              umma_commit_mc2(bar_empty + 8 * stage, 3);
+              if (kb == num_kb - 1) umma_commit_mc2(bar_tfull + 8 * acc, 3);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int e = warp - 2;
+    const int quarter = warp & 3;                 // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+    constexpr int COL_GROUPS = EPI_WARPS / 4;
+    constexpr int COLS_PER_WARP = BN / COL_GROUPS;
+    const int col_begin = (e / 4) * COLS_PER_WARP;
+    float* stg = stg_all + e * 32 * STG_LD;
+    const int rr = lane >> 3;          // row within a 4-row group (transposed phase)
+    const int c4 = (lane & 7) * 4;     // 4 consecutive columns owned in the transposed phase
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int mb = tile / g.num_n_blocks, nb = tile % g.num_n_blocks;
+      const int row0 = (mb * CG + (int)cta_rank) * BM + quarter * 32;
+      const int col0 = nb * BN + col_begin;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + col_begin;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += EPI_COLS) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c, v);
+        tmem_ld_wait();
+        if (c + EPI_COLS >= COLS_PER_WARP) {
+          // all of this warp's accumulator columns are in registers: hand the stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(bar_tempty + 8 * acc);
+            else mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
+          }
+        }
+        // stage: thread = row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+        }
+        __syncwarp();
+        // transposed: 8 lanes cover the 32 columns of one row, 4 rows per instruction
+        const int gcol = col0 + c + c4;
+        const bool col_ok = gcol < g.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr && col_ok) b4 = *reinterpret_cast<const float4*>(g.bias + gcol);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rr;
+          const int grow = row0 + r;
+          float4 a = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          if (grow < g.M && col_ok) {
+            if constexpr (EPI == CACO_EPI_BIAS_RESID_F32) {
+              const float4 rs = *reinterpret_cast<const float4*>(g.resid + (size_t)grow * g.ldr + gcol);
+              a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
+            }
+            if constexpr (EPI == CACO_EPI_BIAS_SILU_F16) { a.x = act_silu(a.x); a.y = act_silu(a.y); a.z = act_silu(a.z); a.w = act_silu(a.w); }
+            if constexpr (EPI == CACO_EPI_BIAS_GELU_F16) { a.x = act_gelu(a.x); a.y = act_gelu(a.y); a.z = act_gelu(a.z); a.w = act_gelu(a.w); }
+            if constexpr (EPI == CACO_EPI_BIAS_F32 || EPI == CACO_EPI_BIAS_RESID_F32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)grow * g.ldo + gcol) = a;
+            } else {
+              __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.out) + (size_t)grow * g.ldo + gcol) = u;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major fp16 matrix [rows, cols] with leading dimension ld (elements); box = [box_rows, 64] with 128B swizzle.
+int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return CACO_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) return CACO_ERR_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<CG, BN, STAGES, EPI_WARPS>;
+  auto kern = gemm_f16_kernel<CG, BN, STAGES, EPI_WARPS, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = g.num_m_blocks * g.num_n_blocks;
+  int ctas = num_sms();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  int groups = ctas / CG;
+  if (groups > tiles) groups = tiles;
+  if (groups < 1) groups = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
+  count_launch();
+  return (int)e;
+}
+
+template <int CG, int BN, int STAGES, int EPI_WARPS>
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas, cudaStream_t s) {
+  switch (epi) {
+    case CACO_EPI_BIAS_F16: return launch_cfg<CG, BN, STAGES, EPI_WARPS, CACO_EPI_BIAS_F16>(ta, tb, g, max_ctas, s);
+    case CACO_EPI_BIAS_SILU_F16: return launch_cfg<CG, BN, STAGES, EPI_WARPS, CACO_EPI_BIAS_SILU_F16>(ta, tb, g, max_ctas, s);
+    case CACO_EPI_BIAS_GELU_F16: return launch_cfg<CG, BN, STAGES, EPI_WARPS, CACO_EPI_BIAS_GELU_F16>(ta, tb, g, max_ctas, s);
+    case CACO_EPI_BIAS_F32: return launch_cfg<CG, BN, STAGES, EPI_WARPS, CACO_EPI_BIAS_F32>(ta, tb, g, max_ctas, s);
+    case CACO_EPI_BIAS_RESID_F32: return launch_cfg<CG, BN, STAGES, EPI_WARPS, CACO_EPI_BIAS_RESID_F32>(ta, tb, g, max_ctas, s);
+  }
+  return CACO_ERR_ARG;
+}
+
+static int g_gemm_variant = 0;  // 0 = auto
+
+int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
+             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
+  if ((N & 3) || (K & 7) || (ldo & 3)) return CACO_ERR_ARG;
+  if (epi == CACO_EPI_BIAS_RESID_F32 && (resid == nullptr || (ldr & 3))) return CACO_ERR_ARG;
+  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG1_N256;
+  const int cg = (variant == CACO_GEMM_CG2_N256) ? 2 : 1;
+  const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.ldo = ldo; g.ldr = ldr; g.bias = bias; g.resid = resid; g.out = out;
+  g.num_m_blocks = (M + BM * cg - 1) / (BM * cg);
+  g.num_n_blocks = (N + bn - 1) / bn;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_f16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_f16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / cg));
+  if (rc) return rc;
+  switch (variant) {
+    case CACO_GEMM_CG1_N256: return launch_epi<1, 256, 4, 4>(epi, ta, tb, g, max_ctas, stream);
+    case CACO_GEMM_CG1_N128: return launch_epi<1, 128, 6, 4>(epi, ta, tb, g, max_ctas, stream);
+    case CACO_GEMM_CG2_N256: return launch_epi<2, 256, 5, 8>(epi, ta, tb, g, max_ctas, stream);
+  }
+  return CACO_ERR_ARG;
+}
+
+}  // namespace caco
+
+extern "C" int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid,
+                             int ldr, void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream) {
+  return caco::gemm_f16(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, epi, variant, 0, (cudaStream_t)stream);
+}
+
+extern "C" void caco_set_gemm_variant(int variant) { caco::g_gemm_variant = variant; }

@@ -1,0 +1,483 @@
+// HBM-bound row kernels of the path: fp32->fp16 cast, LayerNorm (K4), audio position embedding,
+// RoBERTa embedding + LayerNorm (K5), masked single-query attention pooling with optional fused final
+// LayerNorm (K6), L2 normalisation (K7), and a small fp32 GEMM for the [batch, *] tails and the
+// similarity matrix (K8).  One warp per row, 128-bit loads, warp-shuffle reductions; statistics and
+// accumulation in fp32 (two-pass variance, like torch's native_layer_norm).
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "caco_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace caco {
+
+std::atomic<int64_t> g_launches{0};
+
+constexpr int ROW_MAX_V4 = 8;  // per-lane float4 registers: dim <= 1024, dim % 128 == 0
+
+// ------------------------------------------------------------------------------------------------ cast
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = u;
+  } else {
+    for (int64_t k = i; k < n; ++k) dst[k] = __float2half_rn(src[k]);
+  }
+}
+int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (!src || !dst || n <= 0) return CACO_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return CACO_ERR_ALIGN;
+  const int64_t threads = (n + 3) / 4;
+  cast_f32_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(src, (__half*)dst, n);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ row helpers
+struct RowStats { float mean, rstd; };
+
+// v: this lane's float4 chunks of one row (chunk c covers columns c*128 + lane*4 .. +3)
+__device__ __forceinline__ RowStats row_stats(const float4 (&v)[ROW_MAX_V4], int nv, int dim, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) {
+      const float a = v[c].x - mean, b = v[c].y - mean, d = v[c].z - mean, e = v[c].w - mean;
+      q += (a * a + b * b) + (d * d + e * e);
+    }
+  const float var = warp_sum(q) / (float)dim;
+  RowStats r;
+  r.mean = mean;
+  r.rstd = rsqrtf(var + eps);
+  return r;
+}
+
+__device__ __forceinline__ void store_row(const float4& y, float* o32, __half* o16, size_t off) {
+  if (o32) *reinterpret_cast<float4*>(o32 + off) = y;
+  if (o16) {
+    __half2 a = __floats2half2_rn(y.x, y.y), b = __floats2half2_rn(y.z, y.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(o16 + off) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 LayerNorm
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 float* __restrict__ o32, __half* __restrict__ o16, int rows, int dim) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = dim / 128;
+  float4 v[ROW_MAX_V4];
+  const float* xr = x + (size_t)row * dim;
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) v[c] = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4);
+  const RowStats st = row_stats(v, nv, dim, eps);
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) {
+      const int col = c * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+      float4 y;
+      y.x = (v[c].x - st.mean) * st.rstd * g.x + bt.x;
+      y.y = (v[c].y - st.mean) * st.rstd * g.y + bt.y;
+      y.z = (v[c].z - st.mean) * st.rstd * g.z + bt.z;
+      y.w = (v[c].w - st.mean) * st.rstd * g.w + bt.w;
+      store_row(y, o32, o16, (size_t)row * dim + col);
+    }
+}
+int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
+              int dim, cudaStream_t stream) {
+  if (!x || !gamma || !beta || rows <= 0 || dim <= 0 || (dim % 128) || dim > 128 * ROW_MAX_V4) return CACO_ERR_ARG;
+  if (!out_f32 && !out_f16) return CACO_ERR_ARG;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out_f32, (__half*)out_f16, rows, dim);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ audio pos-emb
+// mae.py:102-109: angle = t * exp(2i * (-ln 1e4) / dim); x += cat[sin, cos];  mae.py:136-142: x += freq_emb[f]
+__global__ void __launch_bounds__(256)
+audio_add_pos_kernel(float* __restrict__ x, const float* __restrict__ time_inds, const float* __restrict__ freq_inds,
+                     const float* __restrict__ freq_emb, int n_freq, int rows, int dim) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float t = time_inds[row];
+  int f = (int)freq_inds[row];   // .long() truncation
+  f = min(max(f, 0), n_freq - 1);
+  const int half = dim / 2;
+  float* xr = x + (size_t)row * dim;
+  const float* fe = freq_emb + (size_t)f * dim;
+  for (int i = lane; i < half; i += 32) {
+    const float w = expf(((2.0f * (float)i) * -9.210340371976184f) / (float)dim);
+    float sn, cs;
+    sincosf(t * w, &sn, &cs);
+    xr[i] = (xr[i] + sn) + fe[i];
+    xr[i + half] = (xr[i + half] + cs) + fe[i + half];
+  }
+}
+int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
+                  int dim, cudaStream_t stream) {
+  if (!x || !time_inds || !freq_inds || !freq_emb || rows <= 0 || dim <= 0 || (dim & 1)) return CACO_ERR_ARG;
+  audio_add_pos_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ K5 text embed + LN
+__global__ void __launch_bounds__(256)
+text_embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pids, const float* __restrict__ word,
+                     const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float* __restrict__ o32, __half* __restrict__ o16,
+                     int rows, int T, int dim, int vocab, int max_pos) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int64_t id = ids[row];
+  int64_t pid = pids ? pids[row] : (int64_t)(row % T);   // roberta.py:292-293: arange(T)
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  pid = pid < 0 ? 0 : (pid >= max_pos ? max_pos - 1 : pid);
+  const int nv = dim / 128;
+  float4 v[ROW_MAX_V4];
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) {
+      const int col = c * 128 + lane * 4;
+      const float4 a = *reinterpret_cast<const float4*>(word + (size_t)id * dim + col);
+      const float4 p = *reinterpret_cast<const float4*>(pos + (size_t)pid * dim + col);
+      const float4 ty = *reinterpret_cast<const float4*>(type0 + col);
+      v[c] = make_float4((a.x + p.x) + ty.x, (a.y + p.y) + ty.y, (a.z + p.z) + ty.z, (a.w + p.w) + ty.w);
+    }
+  const RowStats st = row_stats(v, nv, dim, eps);
+#pragma unroll
+  for (int c = 0; c < ROW_MAX_V4; ++c)
+    if (c < nv) {
+      const int col = c * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+      float4 y;
+      y.x = (v[c].x - st.mean) * st.rstd * g.x + bt.x;
+      y.y = (v[c].y - st.mean) * st.rstd * g.y + bt.y;
+      y.z = (v[c].z - st.mean) * st.rstd * g.z + bt.z;
+      y.w = (v[c].w - st.mean) * st.rstd * g.w + bt.w;
+      store_row(y, o32, o16, (size_t)row * dim + col);
+    }
+}
+int text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
+                  const float* type0, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
+                  int batch, int T, int dim, int vocab, int max_pos, cudaStream_t stream) {
+  if (!ids || !word || !pos || !type0 || !gamma || !beta || batch <= 0 || T <= 0) return CACO_ERR_ARG;
+  if ((dim % 128) || dim > 128 * ROW_MAX_V4 || (!out_f32 && !out_f16)) return CACO_ERR_ARG;
+  const int rows = batch * T;
+  text_embed_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, position_ids, word, pos, type0, gamma, beta, eps, out_f32,
+                                                           (__half*)out_f16, rows, T, dim, vocab, max_pos);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ K6 attention pool
+// One CTA (256 threads) per sample.  Phase 1: per token row (one warp each) optional LayerNorm, scores against the
+// folded queries u[h].  Phase 2: masked softmax per head.  Phase 3: weighted sum of the (normalised) rows.
+constexpr int POOL_MAX_HEADS = 4;
+__global__ void __launch_bounds__(256)
+attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, const float* __restrict__ u,
+                 const float* __restrict__ cvec, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+                 float* __restrict__ hid_out, float* __restrict__ pooled, int S, int heads, int dim) {
+  extern __shared__ float sm[];
+  float* s_score = sm;                  // [heads][S]
+  float* s_mean = sm + heads * S;       // [S]
+  float* s_rstd = s_mean + S;           // [S]
+  __shared__ float s_red[POOL_MAX_HEADS][8];
+  __shared__ float s_stat[POOL_MAX_HEADS][2];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* hb = hid + (size_t)b * S * dim;
+  const float* mb = mask + (size_t)b * S;
+  const int nv = dim / 128;
+  const bool do_ln = ln_g != nullptr;
+
+  for (int j = warp; j < S; j += 8) {
+    float4 v[ROW_MAX_V4];
+#pragma unroll
+    for (int c = 0; c < ROW_MAX_V4; ++c)
+      if (c < nv) v[c] = *reinterpret_cast<const float4*>(hb + (size_t)j * dim + c * 128 + lane * 4);
+    RowStats st;
+    st.mean = 0.f; st.rstd = 1.f;
+    if (do_ln) {
+      st = row_stats(v, nv, dim, eps);
+#pragma unroll
+      for (int c = 0; c < ROW_MAX_V4; ++c)
+        if (c < nv) {
+          const int col = c * 128 + lane * 4;
+          const float4 g = *reinterpret_cast<const float4*>(ln_g + col);
+          const float4 bt = *reinterpret_cast<const float4*>(ln_b + col);
+          v[c].x = (v[c].x - st.mean) * st.rstd * g.x + bt.x;
+          v[c].y = (v[c].y - st.mean) * st.rstd * g.y + bt.y;
+          v[c].z = (v[c].z - st.mean) * st.rstd * g.z + bt.z;
+          v[c].w = (v[c].w - st.mean) * st.rstd * g.w + bt.w;
+          if (hid_out) *reinterpret_cast<float4*>(hid_out + ((size_t)b * S + j) * dim + col) = v[c];
+        }
+    }
+    for (int h = 0; h < heads; ++h) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < ROW_MAX_V4; ++c)
+        if (c < nv) {
+          const float4 uu = *reinterpret_cast<const float4*>(u + (size_t)h * dim + c * 128 + lane * 4);
+          d += (v[c].x * uu.x + v[c].y * uu.y) + (v[c].z * uu.z + v[c].w * uu.w);
+        }
+      d = warp_sum(d);
+      if (lane == 0) s_score[h * S + j] = (mb[j] != 0.0f) ? d + cvec[h] : -INFINITY;
+    }
+    if (lane == 0) { s_mean[j] = st.mean; s_rstd[j] = st.rstd; }
+  }
+  __syncthreads();
+  // softmax per head (max, exp, sum) over S
+  for (int h = 0; h < heads; ++h) {
+    float mx = -INFINITY;
+    for (int j = tid; j < S; j += 256) mx = fmaxf(mx, s_score[h * S + j]);
+    mx = warp_max(mx);
+    if (lane == 0) s_red[h][warp] = mx;
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float mx = -INFINITY;
+    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_red[tid][w]);
+    s_stat[tid][0] = mx;
+  }
+  __syncthreads();
+  for (int h = 0; h < heads; ++h) {
+    const float mx = s_stat[h][0];
+    float sum = 0.f;
+    for (int j = tid; j < S; j += 256) {
+      const float e = expf(s_score[h * S + j] - mx);
+      s_score[h * S + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[h][warp] = sum;
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float sum = 0.f;
+    for (int w = 0; w < 8; ++w) sum += s_red[tid][w];
+    s_stat[tid][1] = 1.0f / sum;
+  }
+  __syncthreads();
+  // weighted sum: thread owns columns tid, tid+256, ...
+  for (int col = tid; col < dim; col += 256) {
+    float acc[POOL_MAX_HEADS];
+#pragma unroll
+    for (int h = 0; h < POOL_MAX_HEADS; ++h) acc[h] = 0.f;
+    const float g = do_ln ? ln_g[col] : 1.f, bt = do_ln ? ln_b[col] : 0.f;
+    for (int j = 0; j < S; ++j) {
+      float xv = hb[(size_t)j * dim + col];
+      if (do_ln) xv = (xv - s_mean[j]) * s_rstd[j] * g + bt;
+#pragma unroll
+      for (int h = 0; h < POOL_MAX_HEADS; ++h)
+        if (h < heads) acc[h] = fmaf(s_score[h * S + j], xv, acc[h]);
+    }
+    for (int h = 0; h < heads; ++h) pooled[((size_t)b * heads + h) * dim + col] = acc[h] * s_stat[h][1];
+  }
+}
+int attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
+              const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads, int dim,
+              cudaStream_t stream) {
+  if (!hid || !mask || !u || !c || !pooled || batch <= 0 || seq <= 0 || heads <= 0 || heads > POOL_MAX_HEADS)
+    return CACO_ERR_ARG;
+  if ((dim % 128) || dim > 128 * ROW_MAX_V4) return CACO_ERR_ARG;
+  const size_t smem = (size_t)(heads + 2) * seq * sizeof(float);
+  if (smem > 200 * 1024) return CACO_ERR_ARG;
+  static size_t cur_max = 48 * 1024;
+  if (smem > cur_max) {
+    cudaError_t e = cudaFuncSetAttribute(attn_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return (int)e;
+    cur_max = smem;
+  }
+  attn_pool_kernel<<<batch, 256, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, heads, dim);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// fold a pooler's key projection into its (fixed) query: u[h,i] = sum_d qs[h,d] Wk[h*dh+d, i], c[h] = sum_d qs[h,d] bk[h*dh+d]
+// with qs = query * qscale (caco.py:61-62: 1/sqrt(dh); roberta.py:259: 1/sqrt(hidden)).
+__global__ void fold_query_kernel(const float* __restrict__ query, const float* __restrict__ wk, const float* __restrict__ bk,
+                                  float qscale, float* __restrict__ u, float* __restrict__ c, int heads, int dh, int dim) {
+  const int h = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim) {
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(query[h * dh + d] * qscale, wk[(size_t)(h * dh + d) * dim + i], acc);
+    u[(size_t)h * dim + i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(query[h * dh + d] * qscale, bk[h * dh + d], acc);
+    c[h] = acc;
+  }
+}
+int fold_query(const float* query, const float* wk, const float* bk, float qscale, float* u, float* c, int heads, int dh,
+               int dim, cudaStream_t stream) {
+  dim3 grid((dim + 127) / 128, heads);
+  fold_query_kernel<<<grid, 128, 0, stream>>>(query, wk, bk, qscale, u, c, heads, dh, dim);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ small fp32 GEMM
+// out[M,N] = alpha * A[M,K] · W[N,K]^T + bias.  64x64 tile, 256 threads, 4x4 micro-tile, K step 16.
+// alpha = alpha_scalar * (log_alpha ? exp(*log_alpha) : 1).
+__global__ void __launch_bounds__(256)
+sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                float alpha, const float* __restrict__ log_alpha, float* __restrict__ out, int ldo, int M, int N, int K) {
+  __shared__ float sA[16][64 + 4];
+  __shared__ float sW[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2;          // 0..63: tile row loaded by this thread
+  const int lk = (tid & 3) * 4;     // 0,4,8,12: k offset
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
+    if (m0 + lr < M) {
+      const float* p = A + (size_t)(m0 + lr) * lda + k0 + lk;
+      if (k0 + lk + 3 < K) a = *reinterpret_cast<const float4*>(p);
+      else { if (k0 + lk < K) a.x = p[0]; if (k0 + lk + 1 < K) a.y = p[1]; if (k0 + lk + 2 < K) a.z = p[2]; }
+    }
+    if (n0 + lr < N) {
+      const float* p = W + (size_t)(n0 + lr) * ldw + k0 + lk;
+      if (k0 + lk + 3 < K) w = *reinterpret_cast<const float4*>(p);
+      else { if (k0 + lk < K) w.x = p[0]; if (k0 + lk + 1 < K) w.y = p[1]; if (k0 + lk + 2 < K) w.z = p[2]; }
+    }
+    sA[lk][lr] = a.x; sA[lk + 1][lr] = a.y; sA[lk + 2][lr] = a.z; sA[lk + 3][lr] = a.w;
+    sW[lk][lr] = w.x; sW[lk + 1][lr] = w.y; sW[lk + 2][lr] = w.z; sW[lk + 3][lr] = w.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float al = alpha * (log_alpha ? expf(*log_alpha) : 1.0f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) out[(size_t)m * ldo + n] = al * acc[i][j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+static int sgemm_impl(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha,
+                      const float* log_alpha, float* out, int ldo, int M, int N, int K, cudaStream_t stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
+  if ((lda & 3) || (ldw & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return CACO_ERR_ALIGN;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_nt_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, alpha, log_alpha, out, ldo, M, N, K);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha, float* out, int ldo,
+             int M, int N, int K, cudaStream_t stream) {
+  return sgemm_impl(A, lda, W, ldw, bias, alpha, nullptr, out, ldo, M, N, K, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ K7 / K8
+__global__ void __launch_bounds__(256)
+l2norm_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int dim, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = in + (size_t)row * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) { const float v = x[i] + eps; s = fmaf(v, v, s); }   // caco.py:146: ||e + 1e-10||
+  s = warp_sum(s);
+  const float nrm = sqrtf(s);
+  for (int i = lane; i < dim; i += 32) out[(size_t)row * dim + i] = x[i] / nrm;
+}
+int l2norm(const float* in, float* out, int rows, int dim, float eps, cudaStream_t stream) {
+  if (!in || !out || rows <= 0 || dim <= 0) return CACO_ERR_ARG;
+  l2norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(in, out, rows, dim, eps);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt, int dim,
+               cudaStream_t stream) {
+  if (!a || !t || !logit_scale || !at) return CACO_ERR_ARG;
+  int rc = sgemm_impl(a, dim, t, dim, nullptr, 1.0f, logit_scale, at, nt, na, nt, dim, stream);
+  if (rc || !ta) return rc;
+  return sgemm_impl(t, dim, a, dim, nullptr, 1.0f, logit_scale, ta, na, nt, na, dim, stream);
+}
+
+}  // namespace caco
+
+extern "C" {
+int caco_version(void) { return 100; }
+int caco_built_arch(void) { return 100; }
+int64_t caco_launch_count(void) { return caco::g_launches.load(); }
+int caco_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream) { return caco::cast_f32_f16(src, dst, n, (cudaStream_t)stream); }
+int caco_layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
+                   int dim, void* stream) {
+  return caco::layernorm(x, gamma, beta, eps, out_f32, out_f16, rows, dim, (cudaStream_t)stream);
+}
+int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
+                       int dim, void* stream) {
+  return caco::audio_add_pos(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim, (cudaStream_t)stream);
+}
+int caco_text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
+                       const float* type0, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
+                       int batch, int T, int dim, int vocab, int max_pos, void* stream) {
+  return caco::text_embed_ln(ids, position_ids, word, pos, type0, gamma, beta, eps, out_f32, out_f16, batch, T, dim, vocab,
+                             max_pos, (cudaStream_t)stream);
+}
+int caco_attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
+                   const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads, int dim,
+                   void* stream) {
+  return caco::attn_pool(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, heads, dim,
+                         (cudaStream_t)stream);
+}
+int caco_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha, float* out, int ldo,
+                  int M, int N, int K, void* stream) {
+  return caco::sgemm_nt(A, lda, W, ldw, bias, alpha, out, ldo, M, N, K, (cudaStream_t)stream);
+}
+int caco_l2norm(const float* in, float* out, int rows, int dim, float eps, void* stream) {
+  return caco::l2norm(in, out, rows, dim, eps, (cudaStream_t)stream);
+}
+int caco_sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt, int dim,
+                    void* stream) {
+  return caco::sim_logits(a, t, logit_scale, at, ta, na, nt, dim, (cudaStream_t)stream);
+}
+}

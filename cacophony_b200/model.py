@@ -1,0 +1,410 @@
+"""Host-side mirror of the reference model API (src/caco_torch/caco.py, audio_models/mae.py, text_models/roberta.py).
+
+Same class names, dataclass fields, method names, keyword arguments, defaults, return arity and ``state_dict``
+keys as the reference, so ``from cacophony_b200 import create_caco_model`` replaces
+``from src.caco_torch import create_caco_model`` for the inference path.  The modules below are parameter
+containers only: all arithmetic happens in libcaco_b200.so (hand-written sm_100a kernels) behind a C handle
+(``caco_model_*`` in include/caco_b200.h).  There is no torch-math forward and no CPU fallback: calling a
+model whose parameters are not on a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+NORM_EPS = 1e-10                       # caco.py:14
+
+
+@dataclass
+class AudioTransformerConfig:          # mae.py:9-20
+    hidden_size: int
+    num_layers: int
+    num_heads: int
+    intermediate_size: int
+    patch_size: int
+    max_time_ind: int
+    num_freq_patches: int
+    dropout_rate: float
+    drop_path_rate: float
+    dtype: torch.dtype = torch.float32
+
+
+@dataclass
+class RobertaConfig:                   # roberta.py:11-23
+    vocab_size: int = 50265
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    hidden_dropout_prob: float = 0.1
+    attention_probs_dropout_prob: float = 0.1
+    max_position_embeddings: int = 514
+    type_vocab_size: int = 1
+    layer_norm_eps: float = 1e-5
+    pad_token_id: int = 1
+
+
+@dataclass
+class CACOConfig:                      # caco.py:17-21
+    projection_size: int = 768
+    num_attention_pool_heads: int = 2
+    logit_scale_init_value: float = 2.6592
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter containers (same attribute tree => same state_dict keys as the reference)
+# ------------------------------------------------------------------------------------------------------
+class _Linear(nn.Module):
+    def __init__(self, fan_in: int, fan_out: int):
+        super().__init__()
+        k = 1.0 / fan_in ** 0.5
+        self.weight = nn.Parameter(torch.empty(fan_out, fan_in).uniform_(-k, k), requires_grad=False)
+        self.bias = nn.Parameter(torch.empty(fan_out).uniform_(-k, k), requires_grad=False)
+
+
+class _LayerNorm(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim), requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(dim), requires_grad=False)
+
+
+class _MHA(nn.Module):                 # nn.MultiheadAttention's parameter names (mae.py:69-74)
+    def __init__(self, dim: int):
+        super().__init__()
+        k = (6.0 / (4 * dim)) ** 0.5
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * dim, dim).uniform_(-k, k), requires_grad=False)
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * dim), requires_grad=False)
+        self.out_proj = _Linear(dim, dim)
+
+
+class _MLP(nn.Module):                 # mae.py:47-61
+    def __init__(self, dim: int, ffn: int):
+        super().__init__()
+        self.fc1 = _Linear(dim, ffn)
+        self.fc2 = _Linear(ffn, dim)
+
+
+class AudioEncoderLayer(nn.Module):    # mae.py:64-99
+    def __init__(self, cfg: AudioTransformerConfig):
+        super().__init__()
+        self.norm1 = _LayerNorm(cfg.hidden_size)
+        self.attn = _MHA(cfg.hidden_size)
+        self.norm2 = _LayerNorm(cfg.hidden_size)
+        self.mlp = _MLP(cfg.hidden_size, cfg.intermediate_size)
+
+
+class AudioEncoder(nn.Module):
+    """Parameter tree of mae.py:112-148.  Executed by CACO.get_audio_embedding through the C handle."""
+
+    def __init__(self, config: AudioTransformerConfig):
+        super().__init__()
+        self.config = config
+        self.input_proj = _Linear(config.patch_size, config.hidden_size)
+        self.freq_positional_embedding = nn.Parameter(torch.randn(config.num_freq_patches, config.hidden_size) * 0.02,
+                                                      requires_grad=False)
+        self.layers = nn.ModuleList([AudioEncoderLayer(config) for _ in range(config.num_layers)])
+        self.norm = _LayerNorm(config.hidden_size)
+
+
+class AudioAttentionPooler(nn.Module):
+    """Parameter tree of caco.py:24-79."""
+
+    def __init__(self, hidden_size: int, num_heads: int, projection_size: Optional[int] = None):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = hidden_size // num_heads
+        self.kv_proj = _Linear(hidden_size, 2 * hidden_size)
+        self.out_proj = _Linear(hidden_size, projection_size or hidden_size)
+        self.query = nn.Parameter(torch.randn(hidden_size) * 0.02, requires_grad=False)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, n: int, dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(n, dim), requires_grad=False)
+
+
+class RobertaEmbeddings(nn.Module):    # roberta.py:26-53
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.word_embeddings = _Embedding(cfg.vocab_size, cfg.hidden_size)
+        self.position_embeddings = _Embedding(cfg.max_position_embeddings, cfg.hidden_size)
+        self.token_type_embeddings = _Embedding(cfg.type_vocab_size, cfg.hidden_size)
+        self.LayerNorm = _LayerNorm(cfg.hidden_size)
+
+
+class _SelfAttention(nn.Module):       # roberta.py:56-104
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.query = _Linear(cfg.hidden_size, cfg.hidden_size)
+        self.key = _Linear(cfg.hidden_size, cfg.hidden_size)
+        self.value = _Linear(cfg.hidden_size, cfg.hidden_size)
+
+
+class _DenseLN(nn.Module):             # roberta.py:107-124 / :161-178
+    def __init__(self, fan_in: int, dim: int):
+        super().__init__()
+        self.dense = _Linear(fan_in, dim)
+        self.LayerNorm = _LayerNorm(dim)
+
+
+class _Dense(nn.Module):               # roberta.py:150-158
+    def __init__(self, fan_in: int, fan_out: int):
+        super().__init__()
+        self.dense = _Linear(fan_in, fan_out)
+
+
+class _Attention(nn.Module):
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.self = _SelfAttention(cfg)
+        self.output = _DenseLN(cfg.hidden_size, cfg.hidden_size)
+
+
+class RobertaLayer(nn.Module):         # roberta.py:181-215 (self-attention branch only)
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.attention = _Attention(cfg)
+        self.intermediate = _Dense(cfg.hidden_size, cfg.intermediate_size)
+        self.output = _DenseLN(cfg.intermediate_size, cfg.hidden_size)
+
+
+class RobertaEncoder(nn.Module):       # roberta.py:218-242
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.layers = nn.ModuleList([RobertaLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+
+
+class AttentionPooler(nn.Module):      # roberta.py:245-271
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.attention_pool_query = nn.Parameter(torch.randn(1, cfg.hidden_size) * 0.02, requires_grad=False)
+        self.key_proj = _Linear(cfg.hidden_size, cfg.hidden_size)
+        self.value_proj = _Linear(cfg.hidden_size, cfg.hidden_size)
+
+
+class RobertaModel(nn.Module):
+    """Parameter tree of roberta.py:274-326.  Executed by CACO.get_text_embedding through the C handle."""
+
+    def __init__(self, config: RobertaConfig):
+        super().__init__()
+        self.config = config
+        self.embeddings = RobertaEmbeddings(config)
+        self.encoder = RobertaEncoder(config)
+        self.pooler = AttentionPooler(config)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CACO
+# ------------------------------------------------------------------------------------------------------
+class CACO(nn.Module):
+    """Drop-in for src/caco_torch/caco.py:82-261 (inference path; the captioning decoder is out of scope:
+    ``decoder_module.*`` checkpoint keys are accepted and ignored, ``get_decoder_logits`` raises the
+    reference's own ValueError)."""
+
+    def __init__(self, audio_config: AudioTransformerConfig, text_config: RobertaConfig, caco_config: CACOConfig,
+                 decoder_config: Optional[RobertaConfig] = None):
+        super().__init__()
+        self.audio_config, self.text_config, self.caco_config = audio_config, text_config, caco_config
+        if caco_config.projection_size != audio_config.hidden_size or text_config.hidden_size != audio_config.hidden_size:
+            raise ValueError("cacophony_b200 supports projection_size == hidden_size for both towers (the checkpoint's shape)")
+        self.audio_module = AudioEncoder(audio_config)
+        self.audio_attention_pool = AudioAttentionPooler(audio_config.hidden_size, caco_config.num_attention_pool_heads,
+                                                         caco_config.projection_size)
+        self.text_module = RobertaModel(text_config)
+        self.text_proj = _Linear(text_config.hidden_size, caco_config.projection_size)
+        self.logit_scale = nn.Parameter(torch.tensor(caco_config.logit_scale_init_value), requires_grad=False)
+        self.decoder_module = None       # caco.py:118-121: captioning head, not on this path
+        self._handle: Optional[int] = None
+        self._packed_key = None
+        self.eval()
+
+    # ---- state handling ---------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts the reference checkpoint layouts' tensors; ``decoder_module.*`` is ignored."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("decoder_module.")}
+        out = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._packed_key = None
+        return out
+
+    def _apply(self, fn, *a, **kw):      # .to() / .cuda() move the parameters -> re-pack lazily
+        self._packed_key = None
+        return super()._apply(fn, *a, **kw)
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                L.load().caco_model_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _device(self) -> torch.device:
+        return self.logit_scale.device
+
+    def _ensure_packed(self) -> int:
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cacophony_b200.CACO runs on a CUDA device only (no CPU fallback): call model.to('cuda')")
+        if self._handle is not None and self._packed_key:
+            return self._handle          # invalidated by load_state_dict / .to(); call repack() after in-place edits
+        sd = self.state_dict()
+        lib = L.load()
+        if self._handle is None:
+            a, t = self.audio_config, self.text_config
+            cfg = L.CacoConfig(a.hidden_size, a.intermediate_size, a.patch_size, a.num_layers, a.num_heads,
+                               a.num_freq_patches, self.caco_config.num_attention_pool_heads, t.num_hidden_layers,
+                               t.num_attention_heads, t.vocab_size, t.max_position_embeddings, float(t.layer_norm_eps))
+            h = C.c_void_p()
+            L.check(lib.caco_model_create(C.byref(cfg), C.byref(h)), "caco_model_create")
+            self._handle = h.value
+        with torch.cuda.device(dev):
+            for k, v in sd.items():
+                if v.dtype != torch.float32 or not v.is_contiguous():
+                    raise ValueError(f"parameter {k}: expected contiguous float32")
+                rc = lib.caco_model_set_tensor(self._handle, k.encode(), v.data_ptr(), v.numel())
+                if rc < 0:
+                    L.check(rc, f"caco_model_set_tensor({k})")
+            L.check(lib.caco_model_pack(self._handle, L.stream_ptr()), "caco_model_pack")
+        self._packed_key = True
+        return self._handle
+
+    def repack(self) -> None:
+        """Re-read the parameters (needed only after modifying them in place)."""
+        self._packed_key = None
+        self._ensure_packed()
+
+    # ---- reference API ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_audio_embedding(self, audio_patches: torch.Tensor, audio_time_inds: torch.Tensor,
+                            audio_freq_inds: torch.Tensor, audio_mask: torch.Tensor, deterministic: bool = True,
+                            return_hidden_state: bool = True, normalize: bool = False
+                            ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        """caco.py:123-150."""
+        if not deterministic:
+            raise ValueError("cacophony_b200 implements the inference path only (deterministic=True)")
+        h = self._ensure_packed()
+        dev = self._device()
+        p = _as(audio_patches, torch.float32, dev, "audio_patches")
+        if p.dim() != 3 or p.shape[-1] != self.audio_config.patch_size:
+            raise ValueError(f"audio_patches: expected [batch, seq, {self.audio_config.patch_size}]")
+        B, S, _ = p.shape
+        ti = _as(audio_time_inds, torch.float32, dev, "audio_time_inds")
+        fi = _as(audio_freq_inds, torch.float32, dev, "audio_freq_inds")
+        mk = _as(audio_mask, torch.float32, dev, "audio_mask")
+        for n, t in (("audio_time_inds", ti), ("audio_freq_inds", fi), ("audio_mask", mk)):
+            if tuple(t.shape) != (B, S):
+                raise ValueError(f"{n}: expected shape {(B, S)}, got {tuple(t.shape)}")
+        D = self.audio_config.hidden_size
+        emb = torch.empty((B, D), dtype=torch.float32, device=dev)
+        hid = torch.empty((B, S, D), dtype=torch.float32, device=dev) if return_hidden_state else None
+        with torch.cuda.device(dev):
+            L.check(L.load().caco_model_audio_embedding(h, L.ptr(p), L.ptr(ti), L.ptr(fi), L.ptr(mk), B, S, int(normalize),
+                                                        L.ptr(emb), L.ptr(hid), L.stream_ptr()), "caco_model_audio_embedding")
+        return (emb, hid) if return_hidden_state else emb
+
+    @torch.no_grad()
+    def get_text_embedding(self, text_input_ids: torch.Tensor, text_mask: torch.Tensor,
+                           position_ids: Optional[torch.Tensor] = None, deterministic: bool = True,
+                           return_hidden_state: bool = True, normalize: bool = False
+                           ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        """caco.py:152-177."""
+        if not deterministic:
+            raise ValueError("cacophony_b200 implements the inference path only (deterministic=True)")
+        h = self._ensure_packed()
+        dev = self._device()
+        ids = _as(text_input_ids, torch.int64, dev, "text_input_ids")
+        if ids.dim() != 2:
+            raise ValueError("text_input_ids: expected [batch, seq]")
+        B, T = ids.shape
+        if T > 256 or T > self.text_config.max_position_embeddings:
+            raise ValueError("text sequence length must be <= 256")
+        mk = _as(text_mask, torch.float32, dev, "text_mask")
+        if tuple(mk.shape) != (B, T):
+            raise ValueError(f"text_mask: expected shape {(B, T)}")
+        pids = None if position_ids is None else _as(position_ids, torch.int64, dev, "position_ids").expand(B, T).contiguous()
+        D = self.text_config.hidden_size
+        emb = torch.empty((B, D), dtype=torch.float32, device=dev)
+        hid = torch.empty((B, T, D), dtype=torch.float32, device=dev) if return_hidden_state else None
+        with torch.cuda.device(dev):
+            L.check(L.load().caco_model_text_embedding(h, L.ptr(ids), L.ptr(mk), L.ptr(pids), B, T, int(normalize), L.ptr(emb),
+                                                       L.ptr(hid), L.stream_ptr()), "caco_model_text_embedding")
+        return (emb, hid) if return_hidden_state else emb
+
+    @torch.no_grad()
+    def get_contrastive_logits(self, audio_patches, audio_time_inds, audio_freq_inds, audio_mask, text_input_ids,
+                               text_mask, deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """caco.py:179-212."""
+        a = self.get_audio_embedding(audio_patches, audio_time_inds, audio_freq_inds, audio_mask,
+                                     deterministic=deterministic, return_hidden_state=False, normalize=True)
+        t = self.get_text_embedding(text_input_ids, text_mask, deterministic=deterministic,
+                                    return_hidden_state=False, normalize=True)
+        return self.similarity(a, t)
+
+    def get_decoder_logits(self, *args, **kwargs):
+        raise ValueError("Decoder module not initialized")       # caco.py:223-224
+
+    def forward(self, audio_patches, audio_time_inds, audio_freq_inds, audio_mask, text_input_ids, text_mask,
+                deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """caco.py:242-261."""
+        return self.get_contrastive_logits(audio_patches, audio_time_inds, audio_freq_inds, audio_mask, text_input_ids,
+                                           text_mask, deterministic=deterministic)
+
+    # ---- additions (north-star aliases) -------------------------------------------------------------
+    @torch.no_grad()
+    def similarity(self, audio_embedding: torch.Tensor, text_embedding: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(exp(logit_scale)·A)·Tᵀ and (exp(logit_scale)·T)·Aᵀ (caco.py:208-210) for already-normalised embeddings."""
+        dev = self._device()
+        a = _as(audio_embedding, torch.float32, dev, "audio_embedding")
+        t = _as(text_embedding, torch.float32, dev, "text_embedding")
+        with torch.cuda.device(dev):
+            return ops.sim_logits(a, t, self.logit_scale.data.reshape(1))
+
+    @torch.no_grad()
+    def encode_audio(self, waveform: torch.Tensor, max_patches: int = 500, normalize: bool = True) -> torch.Tensor:
+        """waveform [batch, n_samples] (16 kHz fp32) -> L2-normalised audio embeddings [batch, 768]:
+        prepare_audio_batch (eval_caco_torch.py:181-206) + get_audio_embedding in one library call."""
+        h = self._ensure_packed()
+        dev = self._device()
+        w = _as(waveform, torch.float32, dev, "waveform")
+        if w.dim() == 1:
+            w = w[None]
+        B, n = w.shape
+        emb = torch.empty((B, self.audio_config.hidden_size), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().caco_model_encode_audio(h, L.ptr(w), B, n, max_patches, int(normalize), L.ptr(emb), L.stream_ptr()),
+                    "caco_model_encode_audio")
+        return emb
+
+    @torch.no_grad()
+    def encode_text(self, text_input_ids: torch.Tensor, text_mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+        return self.get_text_embedding(text_input_ids, text_mask, return_hidden_state=False, normalize=normalize)
+
+
+def _as(t: torch.Tensor, dtype, dev, name: str) -> torch.Tensor:
+    """Move/cast an argument the way the reference's torch ops would accept it (e.g. int64 masks), contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name}: expected a torch.Tensor")
+    if t.device != dev:
+        t = t.to(dev)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def create_caco_model() -> CACO:
+    """caco.py:264-317: the checkpoint's configuration."""
+    audio_config = AudioTransformerConfig(hidden_size=768, num_layers=12, num_heads=8, intermediate_size=3072,
+                                          patch_size=256, max_time_ind=512, num_freq_patches=8, dropout_rate=0.0,
+                                          drop_path_rate=0.0)
+    text_config = RobertaConfig()
+    caco_config = CACOConfig()
+    decoder_config = RobertaConfig(num_hidden_layers=4)
+    return CACO(audio_config=audio_config, text_config=text_config, caco_config=caco_config, decoder_config=decoder_config)

@@ -1,0 +1,187 @@
+"""Operator-level Python surface over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function validates device / dtype / contiguity, allocates the output with torch (PyTorch owns all memory),
+and enqueues ONE library call on the current CUDA stream.  Errors are Python exceptions (ValueError for bad
+arguments, CacoError for a failing library call); nothing falls back to torch math.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (cacophony_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    L.check(L.load().caco_cast_f32_f16(L.ptr(x), L.ptr(out), x.numel(), L.stream_ptr()), "caco_cast_f32_f16")
+    return out
+
+
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epi: int,
+             resid: Optional[torch.Tensor] = None, variant: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """epilogue(a[M,K] @ w[N,K].T + bias); a, w fp16; out fp16 (EPI_*_F16) or fp32."""
+    _need(a, torch.float16, "a")
+    _need(w, torch.float16, "w")
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
+        raise ValueError("gemm_f16: a[M,K], w[N,K] expected")
+    M, K = a.shape
+    N = w.shape[0]
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+        if bias.numel() != N:
+            raise ValueError("gemm_f16: bias must have N elements")
+    out_dtype = torch.float32 if epi in (L.EPI_BIAS_F32, L.EPI_BIAS_RESID_F32) else torch.float16
+    if epi == L.EPI_BIAS_RESID_F32:
+        if resid is None:
+            raise ValueError("gemm_f16: EPI_BIAS_RESID_F32 needs resid")
+        _need(resid, torch.float32, "resid")
+        if tuple(resid.shape) != (M, N):
+            raise ValueError("gemm_f16: resid must be [M,N]")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    else:
+        _need(out, out_dtype, "out")
+    rc = L.load().caco_gemm_f16(L.ptr(a), K, L.ptr(w), K, L.ptr(bias), L.ptr(resid), N, L.ptr(out), N, M, N, K, epi,
+                                variant, L.stream_ptr())
+    L.check(rc, "caco_gemm_f16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, want_f32: bool = True,
+              want_f16: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    _need(x, torch.float32, "x"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    o32 = torch.empty_like(x) if want_f32 else None
+    o16 = torch.empty(x.shape, dtype=torch.float16, device=x.device) if want_f16 else None
+    L.check(L.load().caco_layernorm(L.ptr(x), L.ptr(gamma), L.ptr(beta), eps, L.ptr(o32), L.ptr(o16), rows, dim,
+                                    L.stream_ptr()), "caco_layernorm")
+    return o32, o16
+
+
+def audio_add_pos(x: torch.Tensor, time_inds: torch.Tensor, freq_inds: torch.Tensor, freq_emb: torch.Tensor) -> torch.Tensor:
+    """In place: x[m] += sincos(time_inds[m]) + freq_emb[freq_inds[m]] (mae.py:135-142)."""
+    _need(x, torch.float32, "x"); _need(time_inds, torch.float32, "time_inds"); _need(freq_inds, torch.float32, "freq_inds")
+    _need(freq_emb, torch.float32, "freq_emb")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    L.check(L.load().caco_audio_add_pos(L.ptr(x), L.ptr(time_inds), L.ptr(freq_inds), L.ptr(freq_emb), freq_emb.shape[0],
+                                        rows, dim, L.stream_ptr()), "caco_audio_add_pos")
+    return x
+
+
+def attention_audio(qkv: torch.Tensor, mask: torch.Tensor, heads: int) -> torch.Tensor:
+    """qkv [B,S,3*D] fp16 (q|k|v), mask [B,S] fp32 (1 = keep) -> [B,S,D] fp16."""
+    _need(qkv, torch.float16, "qkv"); _need(mask, torch.float32, "mask")
+    B, S, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, S, D), dtype=torch.float16, device=qkv.device)
+    L.check(L.load().caco_attention_audio(L.ptr(qkv), L.ptr(mask), L.ptr(out), B, S, heads, D // heads, L.stream_ptr()),
+            "caco_attention_audio")
+    return out
+
+
+def attention_text(qkv: torch.Tensor, key_mask: torch.Tensor, heads: int) -> torch.Tensor:
+    _need(qkv, torch.float16, "qkv"); _need(key_mask, torch.float32, "key_mask")
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, T, D), dtype=torch.float16, device=qkv.device)
+    L.check(L.load().caco_attention_text(L.ptr(qkv), L.ptr(key_mask), L.ptr(out), B, T, heads, D // heads, L.stream_ptr()),
+            "caco_attention_text")
+    return out
+
+
+def text_embed_ln(ids, position_ids, word, pos, type0, gamma, beta, eps: float = 1e-5):
+    _need(ids, torch.int64, "ids")
+    if position_ids is not None:
+        _need(position_ids, torch.int64, "position_ids")
+    for n, t in (("word", word), ("pos", pos), ("type0", type0), ("gamma", gamma), ("beta", beta)):
+        _need(t, torch.float32, n)
+    B, T = ids.shape
+    dim = word.shape[1]
+    o32 = torch.empty((B, T, dim), dtype=torch.float32, device=ids.device)
+    o16 = torch.empty((B, T, dim), dtype=torch.float16, device=ids.device)
+    L.check(L.load().caco_text_embed_ln(L.ptr(ids), L.ptr(position_ids), L.ptr(word), L.ptr(pos), L.ptr(type0), L.ptr(gamma),
+                                        L.ptr(beta), eps, L.ptr(o32), L.ptr(o16), B, T, dim, word.shape[0], pos.shape[0],
+                                        L.stream_ptr()), "caco_text_embed_ln")
+    return o32, o16
+
+
+def attn_pool(hid, mask, u, c, ln_gamma=None, ln_beta=None, ln_eps: float = 1e-5, want_hidden: bool = False):
+    _need(hid, torch.float32, "hid"); _need(mask, torch.float32, "mask"); _need(u, torch.float32, "u"); _need(c, torch.float32, "c")
+    B, S, dim = hid.shape
+    heads = u.shape[0]
+    pooled = torch.empty((B, heads, dim), dtype=torch.float32, device=hid.device)
+    hid_out = torch.empty_like(hid) if (want_hidden and ln_gamma is not None) else None
+    L.check(L.load().caco_attn_pool(L.ptr(hid), L.ptr(mask), L.ptr(u), L.ptr(c), L.ptr(ln_gamma), L.ptr(ln_beta), ln_eps,
+                                    L.ptr(hid_out), L.ptr(pooled), B, S, heads, dim, L.stream_ptr()), "caco_attn_pool")
+    return pooled, hid_out
+
+
+def sgemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    _need(a, torch.float32, "a"); _need(w, torch.float32, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    L.check(L.load().caco_sgemm_nt(L.ptr(a), K, L.ptr(w), K, L.ptr(bias), alpha, L.ptr(out), N, M, N, K, L.stream_ptr()),
+            "caco_sgemm_nt")
+    return out
+
+
+def l2norm(x: torch.Tensor, eps: float = 1e-10) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    L.check(L.load().caco_l2norm(L.ptr(x), L.ptr(out), x.shape[0], x.shape[1], eps, L.stream_ptr()), "caco_l2norm")
+    return out
+
+
+def sim_logits(a: torch.Tensor, t: torch.Tensor, logit_scale: torch.Tensor, want_ta: bool = True):
+    """(exp(logit_scale)*a) @ t.T and its transpose counterpart (caco.py:208-210)."""
+    _need(a, torch.float32, "a"); _need(t, torch.float32, "t"); _need(logit_scale, torch.float32, "logit_scale")
+    na, dim = a.shape
+    nt = t.shape[0]
+    at = torch.empty((na, nt), dtype=torch.float32, device=a.device)
+    ta = torch.empty((nt, na), dtype=torch.float32, device=a.device) if want_ta else None
+    L.check(L.load().caco_sim_logits(L.ptr(a), L.ptr(t), L.ptr(logit_scale), L.ptr(at), L.ptr(ta), na, nt, dim,
+                                     L.stream_ptr()), "caco_sim_logits")
+    return at, ta
+
+
+def frontend(wave: torch.Tensor, max_patches: int, want_log_mel: bool = False, want_f16: bool = False):
+    """wave [B, L] fp32 CUDA -> dict(audio_patches [B,P,256], audio_time_inds, audio_freq_inds, audio_mask [B,P])."""
+    _need(wave, torch.float32, "wave")
+    if wave.dim() != 2:
+        raise ValueError("frontend: wave must be [batch, n_samples]")
+    B, n = wave.shape
+    dev = wave.device
+    patches = torch.empty((B, max_patches, 256), dtype=torch.float32, device=dev)
+    p16 = torch.empty((B, max_patches, 256), dtype=torch.float16, device=dev) if want_f16 else None
+    ti = torch.empty((B, max_patches), dtype=torch.float32, device=dev)
+    fi = torch.empty_like(ti)
+    mk = torch.empty_like(ti)
+    n_frames = (n + 159) // 160
+    mel = torch.empty((B, n_frames, 128), dtype=torch.float32, device=dev) if want_log_mel else None
+    L.check(L.load().caco_frontend(L.ptr(wave), B, n, max_patches, L.ptr(patches), L.ptr(p16), L.ptr(ti), L.ptr(fi), L.ptr(mk),
+                                   L.ptr(mel), L.stream_ptr()), "caco_frontend")
+    out = {"audio_patches": patches, "audio_time_inds": ti, "audio_freq_inds": fi, "audio_mask": mk}
+    if want_log_mel:
+        out["log_mel"] = mel
+    if want_f16:
+        out["audio_patches_f16"] = p16
+    return out

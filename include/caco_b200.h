@@ -1,0 +1,164 @@
+/* caco_b200.h — C ABI of libcaco_b200.so, the sm_100a implementation of Cacophony's inference hot path.
+ *
+ * The reference (gzhu06/Cacophony, src/caco_torch + the frontend functions of
+ * src/eval/eval_caco_torch.py) is pure Python over torch ops and has no FFI layer of its own; this
+ * header is therefore the boundary a reference maintainer would bind with ctypes (INTEGRATION.md shows
+ * the stub).  Every entry point cites the reference code it replaces (paths relative to the reference
+ * repo root).  Conventions:
+ *   - plain C: raw DEVICE pointers + sizes + a cudaStream_t passed as void*; no torch types;
+ *   - the caller owns all memory; the library only borrows pointers for the duration of the call
+ *     (work is enqueued on `stream`, so buffers must stay alive until the stream has drained);
+ *   - all matrices are dense row-major; "f16" = IEEE binary16, "f32" = binary32;
+ *   - return 0 on success, a CACO_ERR_* (negative) or a cudaError_t (positive) otherwise; nothing
+ *     throws across the boundary and there is NO CPU fallback.
+ */
+#ifndef CACO_B200_H_
+#define CACO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CACO_ERR_ARG (-1)     /* bad shape / null pointer / unsupported size */
+#define CACO_ERR_ALIGN (-2)   /* pointer or leading dimension not 16-byte aligned */
+#define CACO_ERR_DRIVER (-3)  /* cuTensorMapEncodeTiled unavailable or failed */
+#define CACO_ERR_STATE (-4)   /* model handle used before weights were packed, etc. */
+
+/* GEMM epilogues (what is fused after A·Wᵀ) */
+#define CACO_EPI_BIAS_F16 0        /* out_f16 = acc + bias                      (QKV projections)            */
+#define CACO_EPI_BIAS_SILU_F16 1   /* out_f16 = silu(acc + bias)                (mae.py:56-57 fc1+SiLU)      */
+#define CACO_EPI_BIAS_GELU_F16 2   /* out_f16 = gelu_erf(acc + bias)            (roberta.py:156-157)         */
+#define CACO_EPI_BIAS_F32 3        /* out_f32 = acc + bias                      (input_proj mae.py:133)      */
+#define CACO_EPI_BIAS_RESID_F32 4  /* out_f32 = acc + bias + resid_f32          (mae.py:93,97; roberta.py:122,176) */
+
+/* GEMM kernel variants (0 = library default) */
+#define CACO_GEMM_CG1_N256 1  /* one CTA per 128x256 tile, tcgen05.mma.cta_group::1 */
+#define CACO_GEMM_CG1_N128 2  /* one CTA per 128x128 tile */
+#define CACO_GEMM_CG2_N256 3  /* CTA pair per 256x256 tile, tcgen05.mma.cta_group::2 */
+
+/* Library/version probe; also reports the compute capability the kernels were built for (100). */
+int caco_version(void);
+int caco_built_arch(void);
+
+/* ---- K1: waveform -> log-mel -> 16x16 patches  (src/eval/eval_caco_torch.py:41-151, :181-206) ----
+ * wave        [batch, n_samples] f32 (all clips the same length; ragged batches = one call per length)
+ * patches     [batch, max_patches, 256] f32   token p = 8*t+f, element dt*16+df = mel[16t+dt, 16f+df]
+ * patches_f16 same layout in f16 or NULL (operand copy for the input-projection GEMM)
+ * time_inds / freq_inds / mask  [batch, max_patches] f32 (padded slots: index 0, mask 0)
+ * log_mel     optional [batch, ceil(n/160), 128] f32 (compute_mel_spectrogram output) or NULL          */
+int caco_frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
+                  float* time_inds, float* freq_inds, float* mask, float* log_mel, void* stream);
+
+/* ---- K2: out = epilogue(A[M,K] f16 · W[N,K]ᵀ f16), fp32 accumulate on tcgen05 tensor cores.
+ * Replaces every nn.Linear on the path (mae.py:51-52,69,116; roberta.py:62-64,110,153,164; caco.py:35,37).
+ * lda/ldw/ldo/ldr are leading dimensions in ELEMENTS.  N % 4 == 0, K % 8 == 0.                       */
+int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr,
+                  void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream);
+void caco_set_gemm_variant(int variant);
+
+/* f32 -> f16 round-to-nearest copy (weight packing / operand copies). */
+int caco_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- K4: LayerNorm over the last dim (nn.LayerNorm eps=1e-5: mae.py:68,76,123; roberta.py:32,111,165).
+ * y = (x-mean)/sqrt(var+eps)*gamma+beta ; writes y as f32 (out_f32, may be NULL) and/or f16 (out_f16, may be NULL). */
+int caco_layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
+                   int rows, int dim, void* stream);
+
+/* ---- audio position embedding (mae.py:102-109,135-142): x[m,:] += cat[sin(t·w), cos(t·w)] + freq_emb[f[m]]. */
+int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq,
+                       int rows, int dim, void* stream);
+
+/* ---- K3a: audio self-attention, nn.MultiheadAttention semantics (mae.py:69-74,89-92):
+ * qkv [batch*seq, 3*heads*dh] f16 (q|k|v packed in-proj output), q scaled by 1/sqrt(dh) inside,
+ * keys with mask==0 get -inf, softmax in fp32, out [batch*seq, heads*dh] f16.  dh in {64, 96}.            */
+int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
+                         void* stream);
+
+/* ---- K3b: causal text self-attention (roberta.py:86-102, mask from roberta.py:297-310):
+ * qkv [batch*T, 3*heads*64] f16, key_mask [batch, T] f32 (1 = keep); allowed(i,j) = j<=i && key_mask[j]. */
+int caco_attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
+                        void* stream);
+
+/* ---- K5: RoBERTa embeddings + LayerNorm (roberta.py:35-53): LN(word[id] + pos[pid] + type[0]).
+ * position_ids may be NULL (= arange(T), roberta.py:292-293).                                          */
+int caco_text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
+                       const float* type0, const float* gamma, const float* beta, float eps, float* out_f32,
+                       void* out_f16, int batch, int T, int dim, int vocab, int max_pos, void* stream);
+
+/* ---- K6: masked single-query attention pooling over tokens.
+ * scores[b,h,j] = dot(u[h,:], hid[b,j,:]) + c[h]  (the pooler's key projection folded into u, c at pack time),
+ * w = softmax_j(mask(scores)), pooled[b,h,:] = sum_j w[b,h,j] * hid[b,j,:].
+ * If ln_gamma != NULL the rows of `hid` are LayerNorm-ed on the fly (final encoder LN, mae.py:147) and the
+ * normalised rows are also written to hid_out (may be NULL).
+ * Used for AudioAttentionPooler (caco.py:41-79, heads=2) and AttentionPooler (roberta.py:253-271, heads=1). */
+int caco_attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
+                   const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads,
+                   int dim, void* stream);
+
+/* ---- small fp32 GEMM for the [batch, *] tails (pooler value/out projections, text_proj, similarity):
+ * out[M,N] = alpha * A[M,K] · W[N,K]ᵀ + bias   (fp32 FMA, exact-order independent of tensor cores). */
+int caco_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha, float* out,
+                  int ldo, int M, int N, int K, void* stream);
+
+/* ---- K7: e / ||e + 1e-10||_2 per row (caco.py:146,173). in == out allowed. */
+int caco_l2norm(const float* in, float* out, int rows, int dim, float eps, void* stream);
+
+/* ---- K8: at = exp(logit_scale)·A·Tᵀ, ta = atᵀ (caco.py:208-210).  A [na,dim], T [nt,dim] f32.
+ * logit_scale is a DEVICE pointer to the scalar parameter.  ta may be NULL.                          */
+int caco_sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt,
+                    int dim, void* stream);
+
+/* ======================================= model handle ==========================================
+ * A handle owns fp16-packed copies of the encoder weights, folded pooler vectors and an activation
+ * workspace (cudaMalloc); inputs/outputs stay caller-owned.  Mirrors CACO (src/caco_torch/caco.py:82-261). */
+typedef struct caco_model caco_model;
+
+typedef struct {
+  int hidden;        /* 768  */
+  int ffn;           /* 3072 */
+  int patch_dim;     /* 256  */
+  int audio_layers;  /* 12   */
+  int audio_heads;   /* 8    */
+  int n_freq;        /* 8    */
+  int pool_heads;    /* 2  (CACOConfig.num_attention_pool_heads, caco.py:20) */
+  int text_layers;   /* 12   */
+  int text_heads;    /* 12   */
+  int vocab;         /* 50265 */
+  int max_pos;       /* 514  */
+  float ln_eps;      /* 1e-5 */
+} caco_config;
+
+int caco_model_create(const caco_config* cfg, caco_model** out);
+void caco_model_destroy(caco_model* m);
+/* Register one f32 DEVICE tensor of the reference state_dict by its key, e.g.
+ * "audio_module.layers.3.mlp.fc1.weight".  The pointer must stay valid until caco_model_pack returns
+ * for GEMM weights (they are copied to f16) and for the model's lifetime for everything else
+ * (biases, LayerNorm params, embeddings are used in place).  Unknown keys ("decoder_module.*") -> 1. */
+int caco_model_set_tensor(caco_model* m, const char* key, const float* dev_ptr, int64_t numel);
+int caco_model_pack(caco_model* m, void* stream);
+
+/* CACO.get_audio_embedding (caco.py:123-150).  hidden_out [batch, seq, hidden] f32 or NULL. */
+int caco_model_audio_embedding(caco_model* m, const float* patches, const float* time_inds, const float* freq_inds,
+                               const float* mask, int batch, int seq, int normalize, float* emb_out, float* hidden_out,
+                               void* stream);
+/* CACO.get_text_embedding (caco.py:152-177).  mask [batch, T] f32; position_ids may be NULL. */
+int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* mask, const int64_t* position_ids,
+                              int batch, int T, int normalize, float* emb_out, float* hidden_out, void* stream);
+/* waveform-in convenience: frontend + get_audio_embedding in one call (encode_audio). */
+int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
+                            float* emb_out, void* stream);
+/* DEVICE pointer to the registered logit_scale scalar (caco.py:116), for caco_sim_logits. */
+const float* caco_model_logit_scale(caco_model* m);
+/* number of kernels the library has launched since load (bench.py's gpu_launches). */
+int64_t caco_launch_count(void);
+/* last error detail of this thread (e.g. which state_dict key was missing), "" if none. */
+const char* caco_last_error(void);
+/* host-only: the fp32 HTK mel filterbank the frontend uses, out[257][128] (no GPU needed). */
+int caco_mel_filterbank(float* out_257x128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CACO_B200_H_ */

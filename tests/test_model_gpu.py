@@ -1,0 +1,121 @@
+"""GPU: the whole path through the reference-shaped API (cacophony_b200.CACO) against the golden vectors produced by
+the reference itself (tests/golden/model_*.npz, generator: oracle/make_golden.py) — north-star tolerance: 1e-3
+relative on embeddings and similarity logits — and against the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import cacophony_b200 as cb
+from oracle import caco_oracle as O
+from oracle import weights as W
+from oracle.make_golden import MODEL_CASES, case_inputs
+from tests.util import rel_rows
+
+torch.set_grad_enabled(False)
+REL_TOL = 1e-3          # BASELINE.json north_star: embeddings and logits within 1e-3 relative of the reference
+
+
+_MODELS = {}
+
+
+def _model(seed, sharp, synthetic_state_dict):
+    key = (seed, sharp)
+    if key not in _MODELS:
+        _MODELS.clear()
+        m = cb.create_caco_model()
+        m.load_state_dict(synthetic_state_dict(seed, sharp))
+        _MODELS[key] = m.to("cuda")
+    return _MODELS[key]
+
+
+def _audio_batch(waves, max_patches):
+    """ragged clip lengths -> one frontend launch per clip (the reference's own calling pattern), concatenated."""
+    bs = [cb.prepare_audio_batch(torch.from_numpy(w)[None], cb.DatasetConfig(patches_seq_len=max_patches), "cuda") for w in waves]
+    return {k: torch.cat([b[k] for b in bs]) for k in bs[0]}
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_model_matches_reference_golden(name, golden_dir, synthetic_state_dict):
+    c = MODEL_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    waves, ids, mask = case_inputs(c)
+    ab = _audio_batch(waves, c["max_patches"])
+    ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+
+    a_raw, a_hid = model.get_audio_embedding(**ab)
+    a_n = model.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
+    t_raw, t_hid = model.get_text_embedding(ids_t, mask_t)
+    t_n = model.get_text_embedding(ids_t, mask_t, return_hidden_state=False, normalize=True)
+    assert a_raw.shape == (len(waves), 768) and a_hid.shape == (len(waves), c["max_patches"], 768)
+    assert t_raw.shape == (len(ids), 768) and t_hid.shape == (len(ids), c["T"], 768)
+
+    errs = {"audio_emb_raw": rel_rows(a_raw, g["audio_emb_raw"]), "audio_emb": rel_rows(a_n, g["audio_emb"]),
+            "text_emb_raw": rel_rows(t_raw, g["text_emb_raw"]), "text_emb": rel_rows(t_n, g["text_emb"])}
+    print(name, errs)
+    for k, e in errs.items():
+        assert e < REL_TOL, (k, e)
+    # unit norm
+    np.testing.assert_allclose(a_n.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)
+    # hidden states of valid tokens (sub-sampled in the fixture)
+    valid = ab["audio_mask"][:, ::25].bool().cpu().numpy()
+    ah = a_hid[:, ::25, ::16].cpu().numpy()
+    ref = g["audio_hidden_sub"]
+    assert np.abs(ah[valid] - ref[valid]).max() < 2e-2 and \
+        np.linalg.norm(ah[valid] - ref[valid]) / np.linalg.norm(ref[valid]) < 2e-3
+    tv = mask[:, ::4].astype(bool)
+    th = t_hid[:, ::4, ::16].cpu().numpy()
+    assert np.linalg.norm(th[tv] - g["text_hidden_sub"][tv]) / np.linalg.norm(g["text_hidden_sub"][tv]) < 2e-3
+
+    if "at_logits" in g.files:
+        at, ta = model(**ab, text_input_ids=ids_t, text_mask=mask_t)
+        scale = float(np.exp(W.LOGIT_SCALE_INIT))
+        # logits are scale * cosine: 1e-3 relative on unit-norm embeddings = 1e-3 * scale absolute
+        assert np.abs(at.cpu().numpy() - g["at_logits"]).max() < REL_TOL * scale
+        assert np.abs(ta.cpu().numpy() - g["ta_logits"]).max() < REL_TOL * scale
+        assert rel_rows(at, g["at_logits"]) < 5 * REL_TOL or np.abs(at.cpu().numpy() - g["at_logits"]).max() < 2e-3
+    zs = torch.exp(model.logit_scale) * a_n @ t_n.T
+    assert np.abs(zs.cpu().numpy() - g["zs_logits"]).max() < REL_TOL * float(np.exp(W.LOGIT_SCALE_INIT))
+    margin = np.sort(g["zs_logits"], -1)
+    clear = (margin[:, -1] - margin[:, -2]) > 2e-2 if margin.shape[1] > 1 else np.ones(len(margin), bool)
+    assert np.array_equal(zs.argmax(-1).cpu().numpy()[clear], g["zs_top1"][clear])
+
+
+def test_encode_audio_alias_equals_two_step(synthetic_state_dict):
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    w = torch.from_numpy(W.make_waveforms(77, 3, 160000, "noise")).cuda()
+    e1 = model.encode_audio(w, max_patches=500)
+    ab = cb.prepare_audio_batch(w, cb.DatasetConfig(patches_seq_len=500), "cuda")
+    e2 = model.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
+    assert torch.equal(e1, e2)
+    ids, mask = W.make_captions(5, 3, 32, lens=[32, 7, 15])
+    t1 = model.encode_text(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())
+    t2 = model.get_text_embedding(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda(), return_hidden_state=False, normalize=True)
+    assert torch.equal(t1, t2)
+
+
+def test_batch_invariance_and_padding_rows(synthetic_state_dict):
+    """An embedding must not depend on what else is in the batch (independent units)."""
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    w = torch.from_numpy(W.make_waveforms(91, 5, 80000, "noise")).cuda()
+    e_all = model.encode_audio(w)
+    e_one = model.encode_audio(w[2:3])
+    assert rel_rows(e_all[2:3], e_one) < 1e-6
+
+
+def test_errors_mirror_reference_behaviour(synthetic_state_dict):
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    with pytest.raises(ValueError, match="Decoder module not initialized"):
+        model.get_decoder_logits(None, None, None, None)
+    with pytest.raises(ValueError):
+        model.get_audio_embedding(torch.zeros(1, 10, 255).cuda(), torch.zeros(1, 10).cuda(), torch.zeros(1, 10).cuda(),
+                                  torch.ones(1, 10).cuda())
+    with pytest.raises(RuntimeError):
+        cb.create_caco_model().get_text_embedding(torch.zeros(1, 4, dtype=torch.long), torch.ones(1, 4))
