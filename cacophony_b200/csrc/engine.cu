@@ -84,7 +84,7 @@ static int pack(caco_model* m, cudaStream_t st) {
   // ---- sizes
   const int64_t per_layer = 3 * D * D + D * D + 2 * F * D;
   const int64_t n16 = P * D + per_layer * (c.audio_layers + c.text_layers);
-  const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * (D + 1) + 64;
+  const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * D + 4 * 64;
   if (m->arena16) cudaFree(m->arena16);
   if (m->arena32) cudaFree(m->arena32);
   cudaError_t e = cudaMalloc(&m->arena16, n16 * sizeof(__half));
@@ -136,7 +136,7 @@ static int pack(caco_model* m, cudaStream_t st) {
     m->ap_vw = kvw + D * D;
     m->ap_vb = kvb + D;
     m->a_u = p32; p32 += (int64_t)c.pool_heads * D;
-    m->a_c = p32; p32 += c.pool_heads;
+    m->a_c = p32; p32 += 64;   // keep later carves 16-byte aligned (they are read with float4 loads)
     const int dh = (int)D / c.pool_heads;
     CK(fold_query(query, kvw, kvb, 1.0f / sqrtf((float)dh), m->a_u, m->a_c, c.pool_heads, dh, (int)D, st));
   }
@@ -189,7 +189,7 @@ static int pack(caco_model* m, cudaStream_t st) {
     m->logit_scale = need(m, "logit_scale", 1, &rc);
     if (rc) return rc;
     m->t_u = p32; p32 += D;
-    m->t_c = p32; p32 += 1;
+    m->t_c = p32; p32 += 64;
     CK(fold_query(query, kw, kb, 1.0f / sqrtf((float)D), m->t_u, m->t_c, 1, (int)D, (int)D, st));   // roberta.py:259
   }
   m->packed = true;

@@ -55,7 +55,8 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU ex2 + rcp (2-3 ulp; the result is rounded to fp16 right after)
+__device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>
@@ -192,12 +193,45 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + col_begin;
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += EPI_COLS) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c, v);
+      constexpr int NCHUNK = COLS_PER_WARP / EPI_COLS;
+      // software pipeline over the warp's column chunks: the tcgen05.ld of chunk c+1 and the residual
+      // loads of chunk c+1 are in flight while chunk c goes through the smem transpose and out to HBM
+      uint32_t v[32];
+      float4 rs[2][8];
+      tmem_ld_32x32(t_addr, v);
+      if constexpr (EPI == CACO_EPI_BIAS_RESID_F32) {
+        const int gcol = col0 + c4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + rr;
+          rs[0][it] = (grow < g.M && gcol < g.N) ? *reinterpret_cast<const float4*>(g.resid + (size_t)grow * g.ldr + gcol)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        const int c = ci * EPI_COLS;
         tmem_ld_wait();
-        if (c + EPI_COLS >= COLS_PER_WARP) {
+        // stage: thread = row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+        }
+        if (ci + 1 < NCHUNK) {
+          tmem_ld_32x32(t_addr + c + EPI_COLS, v);
+          if constexpr (EPI == CACO_EPI_BIAS_RESID_F32) {
+            const int gcol = col0 + c + EPI_COLS + c4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row0 + it * 4 + rr;
+              rs[(ci + 1) & 1][it] = (grow < g.M && gcol < g.N)
+                                         ? *reinterpret_cast<const float4*>(g.resid + (size_t)grow * g.ldr + gcol)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        } else {
           // all of this warp's accumulator columns are in registers: hand the stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -206,32 +240,25 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             else mbar_arrive_cluster(mapa(bar_tempty + 8 * acc, 0));
           }
         }
-        // stage: thread = row
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                 __uint_as_float(v[4 * j + 3]));
-          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
-        }
         __syncwarp();
         // transposed: 8 lanes cover the 32 columns of one row, 4 rows per instruction
         const int gcol = col0 + c + c4;
         const bool col_ok = gcol < g.N;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr && col_ok) b4 = *reinterpret_cast<const float4*>(g.bias + gcol);
+        if (g.bias != nullptr && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rr;
           const int grow = row0 + r;
           float4 a = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
           a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          if constexpr (EPI == CACO_EPI_BIAS_RESID_F32) {
+            const float4 q = rs[ci & 1][it];
+            a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+          }
+          if constexpr (EPI == CACO_EPI_BIAS_SILU_F16) { a.x = act_silu(a.x); a.y = act_silu(a.y); a.z = act_silu(a.z); a.w = act_silu(a.w); }
+          if constexpr (EPI == CACO_EPI_BIAS_GELU_F16) { a.x = act_gelu(a.x); a.y = act_gelu(a.y); a.z = act_gelu(a.z); a.w = act_gelu(a.w); }
           if (grow < g.M && col_ok) {
-            if constexpr (EPI == CACO_EPI_BIAS_RESID_F32) {
-              const float4 rs = *reinterpret_cast<const float4*>(g.resid + (size_t)grow * g.ldr + gcol);
-              a.x += rs.x; a.y += rs.y; a.z += rs.z; a.w += rs.w;
-            }
-            if constexpr (EPI == CACO_EPI_BIAS_SILU_F16) { a.x = act_silu(a.x); a.y = act_silu(a.y); a.z = act_silu(a.z); a.w = act_silu(a.w); }
-            if constexpr (EPI == CACO_EPI_BIAS_GELU_F16) { a.x = act_gelu(a.x); a.y = act_gelu(a.y); a.z = act_gelu(a.z); a.w = act_gelu(a.w); }
             if constexpr (EPI == CACO_EPI_BIAS_F32 || EPI == CACO_EPI_BIAS_RESID_F32) {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)grow * g.ldo + gcol) = a;
             } else {
@@ -350,7 +377,7 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
   if (M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
   if ((N & 3) || (K & 7) || (ldo & 3)) return CACO_ERR_ARG;
   if (epi == CACO_EPI_BIAS_RESID_F32 && (resid == nullptr || (ldr & 3))) return CACO_ERR_ARG;
-  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG1_N256;
+  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG2_N256;
   const int cg = (variant == CACO_GEMM_CG2_N256) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
   GemmArgs g;
@@ -363,8 +390,8 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
   rc = make_tmap_f16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / cg));
   if (rc) return rc;
   switch (variant) {
-    case CACO_GEMM_CG1_N256: return launch_epi<1, 256, 4, 4>(epi, ta, tb, g, max_ctas, stream);
-    case CACO_GEMM_CG1_N128: return launch_epi<1, 128, 6, 4>(epi, ta, tb, g, max_ctas, stream);
+    case CACO_GEMM_CG1_N256: return launch_epi<1, 256, 3, 8>(epi, ta, tb, g, max_ctas, stream);
+    case CACO_GEMM_CG1_N128: return launch_epi<1, 128, 5, 8>(epi, ta, tb, g, max_ctas, stream);
     case CACO_GEMM_CG2_N256: return launch_epi<2, 256, 5, 8>(epi, ta, tb, g, max_ctas, stream);
   }
   return CACO_ERR_ARG;
