@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "caco_b200.h"
 #include "common.cuh"
@@ -370,14 +372,25 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
   return CACO_ERR_ARG;
 }
 
+int launch_variant(int variant, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas,
+                   cudaStream_t stream);
 static int g_gemm_variant = 0;  // 0 = auto
+
+// ---- optional live profiling (bench.py's roofline leg): CUDA events around every GEMM launch on its stream
+struct GemmProf {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  std::vector<double> flops;
+  size_t used = 0;
+};
+static GemmProf g_prof;
 
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
              int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
   if ((N & 3) || (K & 7) || (ldo & 3)) return CACO_ERR_ARG;
   if (epi == CACO_EPI_BIAS_RESID_F32 && (resid == nullptr || (ldr & 3))) return CACO_ERR_ARG;
-  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG2_N256;
+  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG1_N256;
   const int cg = (variant == CACO_GEMM_CG2_N256) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
   GemmArgs g;
@@ -389,6 +402,27 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
   if (rc) return rc;
   rc = make_tmap_f16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / cg));
   if (rc) return rc;
+  const bool prof = g_prof.on;
+  size_t slot = 0;
+  if (prof) {
+    slot = g_prof.used++;
+    if (slot >= g_prof.ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      g_prof.ev.emplace_back(a, b);
+      g_prof.flops.push_back(0.0);
+    }
+    g_prof.flops[slot] = 2.0 * (double)M * (double)N * (double)K;
+    cudaEventRecord(g_prof.ev[slot].first, stream);
+  }
+  rc = launch_variant(variant, epi, ta, tb, g, max_ctas, stream);
+  if (prof) cudaEventRecord(g_prof.ev[slot].second, stream);
+  return rc;
+}
+
+int launch_variant(int variant, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas,
+                   cudaStream_t stream) {
   switch (variant) {
     case CACO_GEMM_CG1_N256: return launch_epi<1, 256, 3, 8>(epi, ta, tb, g, max_ctas, stream);
     case CACO_GEMM_CG1_N128: return launch_epi<1, 128, 5, 8>(epi, ta, tb, g, max_ctas, stream);
@@ -405,3 +439,22 @@ extern "C" int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, con
 }
 
 extern "C" void caco_set_gemm_variant(int variant) { caco::g_gemm_variant = variant; }
+
+extern "C" void caco_gemm_profile(int enable) {
+  caco::g_prof.on = enable != 0;
+  caco::g_prof.used = 0;
+}
+// Synchronises the device; returns the number of GEMM launches recorded since caco_gemm_profile(1) and their summed
+// device time (ms) and algorithmic FLOPs.
+extern "C" int caco_gemm_profile_read(double* total_ms, double* total_flops) {
+  cudaDeviceSynchronize();
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < caco::g_prof.used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, caco::g_prof.ev[i].first, caco::g_prof.ev[i].second) == cudaSuccess) ms += t;
+    fl += caco::g_prof.flops[i];
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return (int)caco::g_prof.used;
+}

@@ -359,13 +359,14 @@ class CACO(nn.Module):
 
     # ---- additions (north-star aliases) -------------------------------------------------------------
     @torch.no_grad()
-    def similarity(self, audio_embedding: torch.Tensor, text_embedding: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def similarity(self, audio_embedding: torch.Tensor, text_embedding: torch.Tensor, want_ta: bool = True
+                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """(exp(logit_scale)·A)·Tᵀ and (exp(logit_scale)·T)·Aᵀ (caco.py:208-210) for already-normalised embeddings."""
         dev = self._device()
         a = _as(audio_embedding, torch.float32, dev, "audio_embedding")
         t = _as(text_embedding, torch.float32, dev, "text_embedding")
         with torch.cuda.device(dev):
-            return ops.sim_logits(a, t, self.logit_scale.data.reshape(1))
+            return ops.sim_logits(a, t, self.logit_scale.data.reshape(1), want_ta=want_ta)
 
     @torch.no_grad()
     def encode_audio(self, waveform: torch.Tensor, max_patches: int = 500, normalize: bool = True) -> torch.Tensor:

@@ -57,6 +57,11 @@ int caco_frontend(const float* wave, int batch, int n_samples, int max_patches, 
 int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr,
                   void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream);
 void caco_set_gemm_variant(int variant);
+/* live profiling for bench.py: CUDA events around every GEMM launch on its stream.  caco_gemm_profile(1) resets and
+ * starts recording; caco_gemm_profile_read synchronises the device and returns the launch count, summed device
+ * time (ms) and summed algorithmic FLOPs (2*M*N*K). */
+void caco_gemm_profile(int enable);
+int caco_gemm_profile_read(double* total_ms, double* total_flops);
 
 /* f32 -> f16 round-to-nearest copy (weight packing / operand copies). */
 int caco_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream);
