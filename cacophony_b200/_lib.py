@@ -43,6 +43,7 @@ SIGNATURES = {
     "caco_layernorm": (_I, [_P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "caco_audio_add_pos": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "caco_attention_audio": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "caco_set_attention_impl": (None, [_I]),
     "caco_attention_text": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "caco_text_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
     "caco_attn_pool": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P]),

@@ -88,7 +88,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, CG);   // one arrive per producing CTA (+ tx bytes)
+      mbar_init(bar_full + 8 * s, 1);    // one arrive (leader's producer) + the tx bytes of every CTA of the group
       mbar_init(bar_empty + 8 * s, 1);   // one tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
@@ -128,9 +128,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
             tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
           } else {
-            // both CTAs register their bytes on the LEADER's barrier
-            if (leader) mbar_expect_tx(full, Cfg::STAGE_BYTES);
-            else asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(mapa(full, 0)), "r"((uint32_t)Cfg::STAGE_BYTES) : "memory");
+            // the LEADER's barrier counts the bytes of both CTAs; the peer's loads complete_tx on it remotely.  (The
+            // peer can only be one phase ahead after its own empty barrier fired, i.e. after the leader's phase closed.)
+            if (leader) mbar_expect_tx(full, CG * Cfg::STAGE_BYTES);
             tma_load_2d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
             tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
           }

@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // arrive on a barrier that lives in another CTA of the cluster (address from mapa / peer-bit mask)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -117,6 +117,13 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// 3-D tile load (e.g. [clip][token][column]); out-of-bounds elements of any dimension are zero-filled.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
@@ -273,6 +280,17 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major operand tile stored as rows of 64 bytes (32 fp16) with the 64-byte swizzle (TMA SWIZZLE_64B):
+// 8-row groups are 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                           // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor, kind::f16: fp16 A/B, fp32 D, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
   return (1u << 4)                       // D format: F32
@@ -282,6 +300,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_ma
 }
 
 // ----------------------------------------------------------------------------- misc
+__device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, 2^-22 relative error, exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -81,6 +81,9 @@ int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds,
 int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                          void* stream);
 
+/* 0 = default (tcgen05 kernel, head_dim 96), 1 = warp-level mma.sync kernel (head_dim 64 / 96; debugging aid). */
+void caco_set_attention_impl(int impl);
+
 /* ---- K3b: causal text self-attention (roberta.py:86-102, mask from roberta.py:297-310):
  * qkv [batch*T, 3*heads*64] f16, key_mask [batch, T] f32 (1 = keep); allowed(i,j) = j<=i && key_mask[j]. */
 int caco_attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
