@@ -390,7 +390,7 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
   if (M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
   if ((N & 3) || (K & 7) || (ldo & 3)) return CACO_ERR_ARG;
   if (epi == CACO_EPI_BIAS_RESID_F32 && (resid == nullptr || (ldr & 3))) return CACO_ERR_ARG;
-  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG1_N256;
+  if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG2_N256;
   const int cg = (variant == CACO_GEMM_CG2_N256) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
   GemmArgs g;
