@@ -176,8 +176,11 @@ def run_ours(args):
     wave_d, ids_d, mask_d = wave_h.to(dev), ids_h.to(dev), mask_h.to(dev)
 
     def step(w, i, m):
-        a = model.encode_audio(w, max_patches=MAX_PATCHES)
-        t = model.encode_text(i, m)
+        if args.serial_towers:
+            a = model.encode_audio(w, max_patches=MAX_PATCHES)
+            t = model.encode_text(i, m)
+        else:
+            a, t = model.encode_pairs(w, i, m, max_patches=MAX_PATCHES)
         if world > 1:
             return cdist.sharded_contrastive_logits(model, a, t)
         return model.similarity(a, t)
@@ -301,6 +304,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--serial-towers", action="store_true", help="run the text tower after the audio tower on one stream")
     ap.add_argument("--profile", action="store_true", help="profiling run: resident-input region only (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

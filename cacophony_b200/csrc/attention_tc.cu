@@ -25,12 +25,13 @@ namespace caco {
 
 constexpr int TA_BM = 128, TA_BN = 64, TA_DH = 96;
 constexpr uint32_t TA_Q0 = 0, TA_Q1 = 16384;
-constexpr uint32_t TA_K0 = 24576;   // + stage * 8192
-constexpr uint32_t TA_K1 = 40960;   // + stage * 4096
-constexpr uint32_t TA_V = 49152;    // + stage * 16384  (two 64-column blocks, 8192 B apart)
-constexpr uint32_t TA_P = 81920;
-constexpr uint32_t TA_BAR = 98304;
-constexpr uint32_t TA_BIAS = 98304 + 128;
+constexpr int TA_KSTAGES = 3, TA_VSTAGES = 2;
+constexpr uint32_t TA_K0 = 24576;   // + stage * 8192   (3 stages: K_{j+3} is requested as soon as Q K_j^T retires)
+constexpr uint32_t TA_K1 = 49152;   // + stage * 4096
+constexpr uint32_t TA_V = 61440;    // + stage * 16384  (two 64-column blocks, 8192 B apart)
+constexpr uint32_t TA_P = 94208;
+constexpr uint32_t TA_BAR = 110592;
+constexpr uint32_t TA_BIAS = 110592 + 192;
 constexpr uint32_t TA_Q_BYTES = 24576, TA_K_BYTES = 12288, TA_V_BYTES = 16384;
 constexpr uint32_t TA_TMEM_COLS = 256, TA_S_COL = 0, TA_O_COL = 128;
 constexpr float TA_RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -47,12 +48,12 @@ __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                     const __grid_constant__ CUtensorMap map_kv0, const __grid_constant__ CUtensorMap map_k1,
                     const float* __restrict__ mask, __half* __restrict__ out, int S, int H, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];     // swizzled tiles need 1024-byte alignment
+  const uint32_t sb = smem_u32(smem_raw);
+  uint8_t* sg = smem_raw;
   const uint32_t bar = sb + TA_BAR;
-  const uint32_t b_qfull = bar, b_kfull = bar + 8, b_vfull = bar + 24, b_kvempty = bar + 40, b_sfull = bar + 56,
-                 b_sempty = bar + 72, b_pfull = bar + 88, b_pvdone = bar + 96, tmem_slot = bar + 104;
+  const uint32_t b_qfull = bar, b_kfull = bar + 8, b_kempty = bar + 32, b_vfull = bar + 56, b_vempty = bar + 72,
+                 b_sfull = bar + 88, b_sempty = bar + 104, b_pfull = bar + 120, b_pvdone = bar + 128, tmem_slot = bar + 136;
   float* s_bias = reinterpret_cast<float*>(sg + TA_BIAS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -60,19 +61,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_con
   const int n_blocks = (S + TA_BN - 1) / TA_BN;
   const int D = H * TA_DH;
 
+  auto load_k = [&](int j) {
+    const int ks = j % TA_KSTAGES;
+    mbar_expect_tx(b_kfull + 8 * ks, TA_K_BYTES);
+    tma_load_3d(sb + TA_K0 + ks * 8192, &map_kv0, b_kfull + 8 * ks, D + h * TA_DH, j * TA_BN, b);
+    tma_load_3d(sb + TA_K1 + ks * 4096, &map_k1, b_kfull + 8 * ks, D + h * TA_DH + 64, j * TA_BN, b);
+  };
+  auto load_v = [&](int j) {
+    const int vs = j % TA_VSTAGES;
+    mbar_expect_tx(b_vfull + 8 * vs, TA_V_BYTES);
+    tma_load_3d(sb + TA_V + vs * 16384, &map_kv0, b_vfull + 8 * vs, 2 * D + h * TA_DH, j * TA_BN, b);
+    tma_load_3d(sb + TA_V + vs * 16384 + 8192, &map_kv0, b_vfull + 8 * vs, 2 * D + h * TA_DH + 64, j * TA_BN, b);
+  };
   if (tid == 0) {
+    if ((sb & 1023u) != 0) __trap();
     tma_prefetch_desc(&map_q0); tma_prefetch_desc(&map_q1); tma_prefetch_desc(&map_kv0); tma_prefetch_desc(&map_k1);
     mbar_init(b_qfull, 1);
+    for (int s = 0; s < TA_KSTAGES; ++s) { mbar_init(b_kfull + 8 * s, 1); mbar_init(b_kempty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(b_kfull + 8 * s, 1);
       mbar_init(b_vfull + 8 * s, 1);
-      mbar_init(b_kvempty + 8 * s, 1);
+      mbar_init(b_vempty + 8 * s, 1);
       mbar_init(b_sfull + 8 * s, 1);
       mbar_init(b_sempty + 8 * s, 4);
     }
     mbar_init(b_pfull, 4);
     mbar_init(b_pvdone, 1);
     fence_mbar_init();
+    // prologue loads go out before the CTA-wide barrier so their latency overlaps the mask fetch and the TMEM allocation
+    mbar_expect_tx(b_qfull, TA_Q_BYTES);
+    tma_load_3d(sb + TA_Q0, &map_q0, b_qfull, h * TA_DH, q0, b);
+    tma_load_3d(sb + TA_Q1, &map_q1, b_qfull, h * TA_DH + 64, q0, b);
+    for (int j = 0; j < TA_KSTAGES && j < n_blocks; ++j) load_k(j);
+    for (int j = 0; j < TA_VSTAGES && j < n_blocks; ++j) load_v(j);
   }
   if (warp == 1) {
     tmem_alloc<1>(tmem_slot, TA_TMEM_COLS);
@@ -84,25 +104,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sg + TA_BAR + 104);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sg + TA_BAR + 136);
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(b_qfull, TA_Q_BYTES);
-      tma_load_3d(sb + TA_Q0, &map_q0, b_qfull, h * TA_DH, q0, b);
-      tma_load_3d(sb + TA_Q1, &map_q1, b_qfull, h * TA_DH + 64, q0, b);
-    }
+    // ---------------------------------------------------------------- TMA producer (steady state)
+    // V_j's slot frees when P V_{j-2} retires, K_{j+3}'s slot when Q K_j^T retires: both in tensor-pipe order
     for (int j = 0; j < n_blocks; ++j) {
-      const int s = j & 1;
-      if (j >= 2) mbar_wait(b_kvempty + 8 * s, ((j >> 1) + 1) & 1);
-      if (lane == 0) {
-        mbar_expect_tx(b_kfull + 8 * s, TA_K_BYTES);
-        tma_load_3d(sb + TA_K0 + s * 8192, &map_kv0, b_kfull + 8 * s, D + h * TA_DH, j * TA_BN, b);
-        tma_load_3d(sb + TA_K1 + s * 4096, &map_k1, b_kfull + 8 * s, D + h * TA_DH + 64, j * TA_BN, b);
-        mbar_expect_tx(b_vfull + 8 * s, TA_V_BYTES);
-        tma_load_3d(sb + TA_V + s * 16384, &map_kv0, b_vfull + 8 * s, 2 * D + h * TA_DH, j * TA_BN, b);
-        tma_load_3d(sb + TA_V + s * 16384 + 8192, &map_kv0, b_vfull + 8 * s, 2 * D + h * TA_DH + 64, j * TA_BN, b);
+      if (j >= TA_VSTAGES) {
+        mbar_wait(b_vempty + 8 * (j % TA_VSTAGES), ((j / TA_VSTAGES) + 1) & 1);
+        if (lane == 0) load_v(j);
+      }
+      const int jk = j + TA_KSTAGES;
+      if (jk < n_blocks) {
+        mbar_wait(b_kempty + 8 * (jk % TA_KSTAGES), ((jk / TA_KSTAGES) + 1) & 1);
+        if (lane == 0) load_k(jk);
       }
       __syncwarp();
     }
@@ -111,15 +126,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_con
     constexpr uint32_t idesc_qk = umma_idesc_f16(TA_BM, TA_BN);
     constexpr uint32_t idesc_pv = umma_idesc_f16(TA_BM, TA_DH, false, true);   // B = V is MN-major ([key][d])
     auto issue_qk = [&](int j) {
-      const int s = j & 1;
+      const int s = j & 1, ks_ = j % TA_KSTAGES;
       const uint64_t a0 = umma_desc_kmajor_sw128(sb + TA_Q0), a1 = umma_desc_kmajor_sw64(sb + TA_Q1);
-      const uint64_t k0 = umma_desc_kmajor_sw128(sb + TA_K0 + s * 8192), k1 = umma_desc_kmajor_sw64(sb + TA_K1 + s * 4096);
+      const uint64_t k0 = umma_desc_kmajor_sw128(sb + TA_K0 + ks_ * 8192), k1 = umma_desc_kmajor_sw64(sb + TA_K1 + ks_ * 4096);
       const uint32_t d = tmem_base + TA_S_COL + s * TA_BN;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) umma_f16<1>(d, a0 + 2 * ks, k0 + 2 * ks, idesc_qk, ks ? 1u : 0u);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) umma_f16<1>(d, a1 + 2 * ks, k1 + 2 * ks, idesc_qk, 1u);
       umma_commit<1>(b_sfull + 8 * s);
+      umma_commit<1>(b_kempty + 8 * ks_);
     };
     mbar_wait(b_qfull, 0);
     mbar_wait(b_kfull, 0);
@@ -129,7 +145,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_con
     for (int j = 0; j < n_blocks; ++j) {
       if (j + 1 < n_blocks) {
         const int s1 = (j + 1) & 1;
-        mbar_wait(b_kfull + 8 * s1, ((j + 1) >> 1) & 1);
+        mbar_wait(b_kfull + 8 * ((j + 1) % TA_KSTAGES), ((j + 1) / TA_KSTAGES) & 1);
         if (j + 1 >= 2) mbar_wait(b_sempty + 8 * s1, (((j + 1) >> 1) + 1) & 1);
         tc_fence_after();
         if (lane == 0) issue_qk(j + 1);
@@ -147,7 +163,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_con
           umma_f16<1>(tmem_base + TA_O_COL, pa + 2 * ks, vb, idesc_pv, (j | ks) ? 1u : 0u);
         }
         umma_commit<1>(b_pvdone);
-        umma_commit<1>(b_kvempty + 8 * s);
+        umma_commit<1>(b_vempty + 8 * s);
       }
       __syncwarp();
     }
@@ -285,8 +301,8 @@ int attention_audio_tc(const void* qkv, const float* mask, void* out, int batch,
   if (!qkv || !mask || !out || batch <= 0 || seq <= 0 || heads <= 0 || dh != TA_DH) return CACO_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return CACO_ERR_ALIGN;
   const int n_blocks = (seq + TA_BN - 1) / TA_BN;
-  const size_t smem = TA_BIAS + (size_t)n_blocks * TA_BN * 4 + 1024;
-  if (smem > 113 * 1024) return CACO_ERR_ARG;    // two CTAs per SM; seq <= ~3500
+  const size_t smem = TA_BIAS + (size_t)n_blocks * TA_BN * 4;
+  if (smem > 115 * 1024) return CACO_ERR_ARG;    // two CTAs per SM (seq <= 1728)
   const int ld = 3 * heads * dh;
   CUtensorMap mq0, mq1, mkv0, mk1;
   int rc;

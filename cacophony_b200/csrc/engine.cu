@@ -51,8 +51,8 @@ struct caco_model {
   float* arena32 = nullptr;    // packed text qkv biases + folded pooler vectors
   float *a_u = nullptr, *a_c = nullptr, *t_u = nullptr, *t_c = nullptr;
 
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
+  void* ws[2] = {nullptr, nullptr};      // [0] audio tower, [1] text tower: the towers may run on different streams
+  size_t ws_bytes[2] = {0, 0};
 };
 
 namespace caco {
@@ -64,12 +64,12 @@ static const float* need(caco_model* m, const std::string& key, int64_t numel, i
   return it->second.p;
 }
 
-static int ensure_ws(caco_model* m, size_t bytes) {
-  if (bytes <= m->ws_bytes) return 0;
-  if (m->ws) { cudaDeviceSynchronize(); cudaFree(m->ws); m->ws = nullptr; m->ws_bytes = 0; }
-  cudaError_t e = cudaMalloc(&m->ws, bytes);
+static int ensure_ws(caco_model* m, int which, size_t bytes) {
+  if (bytes <= m->ws_bytes[which]) return 0;
+  if (m->ws[which]) { cudaDeviceSynchronize(); cudaFree(m->ws[which]); m->ws[which] = nullptr; m->ws_bytes[which] = 0; }
+  cudaError_t e = cudaMalloc(&m->ws[which], bytes);
   if (e != cudaSuccess) return (int)e;
-  m->ws_bytes = bytes;
+  m->ws_bytes[which] = bytes;
   return 0;
 }
 
@@ -208,8 +208,8 @@ static int audio_chunk(caco_model* m, const float* patches, const float* t_inds,
   const size_t o_x = carve(R * D * 4), o_h = carve(R * D * 2), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2);
   const size_t o_mlp = carve(R * (size_t)F * 2), o_p16 = carve(R * P * 2);
   const size_t o_pool = carve((size_t)B * c.pool_heads * D * 4), o_o = carve((size_t)B * D * 4), o_e = carve((size_t)B * D * 4);
-  CK(ensure_ws(m, off));
-  uint8_t* w = (uint8_t*)m->ws;
+  CK(ensure_ws(m, 0, off));
+  uint8_t* w = (uint8_t*)m->ws[0];
   float* x = (float*)(w + o_x);
   __half* h16 = (__half*)(w + o_h);
   __half* qkv = (__half*)(w + o_qkv);
@@ -283,8 +283,8 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
     const size_t o_x = carve(R * D * 4), o_x16 = carve(R * D * 2), o_a = carve(R * D * 4), o_a16 = carve(R * D * 2);
     const size_t o_tmp = carve(R * D * 4), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2);
     const size_t o_pool = carve((size_t)nb * D * 4), o_v = carve((size_t)nb * D * 4), o_e = carve((size_t)nb * D * 4);
-    CK(ensure_ws(m, off));
-    uint8_t* w = (uint8_t*)m->ws;
+    CK(ensure_ws(m, 1, off));
+    uint8_t* w = (uint8_t*)m->ws[1];
     float* x = (float*)(w + o_x);
     __half* x16 = (__half*)(w + o_x16);
     float* a = (float*)(w + o_a);
@@ -349,7 +349,8 @@ void caco_model_destroy(caco_model* m) {
   cudaDeviceSynchronize();
   if (m->arena16) cudaFree(m->arena16);
   if (m->arena32) cudaFree(m->arena32);
-  if (m->ws) cudaFree(m->ws);
+  for (int i = 0; i < 2; ++i)
+    if (m->ws[i]) cudaFree(m->ws[i]);
   delete m;
 }
 

@@ -388,6 +388,28 @@ class CACO(nn.Module):
     def encode_text(self, text_input_ids: torch.Tensor, text_mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         return self.get_text_embedding(text_input_ids, text_mask, return_hidden_state=False, normalize=normalize)
 
+    @torch.no_grad()
+    def encode_pairs(self, waveform: torch.Tensor, text_input_ids: torch.Tensor, text_mask: torch.Tensor,
+                     max_patches: int = 500) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Both towers of a batch of pairs, L2-normalised.  The text tower (5 % of the FLOPs, small GEMMs) is enqueued on
+        a side stream so its kernels fill the tails of the audio tower's waves; the towers share no buffers (separate
+        workspaces in the C handle).  Returns (audio_embeddings, text_embeddings)."""
+        dev = self._device()
+        self._ensure_packed()
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        ids = _as(text_input_ids, torch.int64, dev, "text_input_ids")
+        mk = _as(text_mask, torch.float32, dev, "text_mask")
+        self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream):
+            t = self.encode_text(ids, mk)
+        a = self.encode_audio(waveform, max_patches=max_patches)
+        cur.wait_stream(self._side_stream)
+        for x in (ids, mk, t):
+            x.record_stream(cur)
+        return a, t
+
 
 def _as(t: torch.Tensor, dtype, dev, name: str) -> torch.Tensor:
     """Move/cast an argument the way the reference's torch ops would accept it (e.g. int64 masks), contiguous."""
