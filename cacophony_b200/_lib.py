@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libcaco_b200.so")
 
 # mirrors of the header's constants
 EPI_BIAS_F16, EPI_BIAS_SILU_F16, EPI_BIAS_GELU_F16, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = range(5)
-GEMM_AUTO, GEMM_CG1_N256, GEMM_CG1_N128, GEMM_CG2_N256 = range(4)
+GEMM_AUTO, GEMM_CG1_N256, GEMM_CG1_N128, GEMM_CG2_N256, GEMM_CG2_N256_E16 = range(5)
 
 _ERR = {-1: "CACO_ERR_ARG (bad shape / null pointer / unsupported size)",
         -2: "CACO_ERR_ALIGN (pointer or leading dimension not 16-byte aligned)",

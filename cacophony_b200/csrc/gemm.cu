@@ -405,7 +405,7 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
   if (f16_out && ((N & 7) || (ldo & 7))) return CACO_ERR_ARG;   // 16-byte row-layout stores of 8 fp16
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15))) return CACO_ERR_ALIGN;
   if (variant == 0) variant = g_gemm_variant ? g_gemm_variant : CACO_GEMM_CG2_N256;
-  const int cg = (variant == CACO_GEMM_CG2_N256) ? 2 : 1;
+  const int cg = (variant == CACO_GEMM_CG2_N256 || variant == CACO_GEMM_CG2_N256_E16) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.ldo = ldo; g.ldr = ldr; g.bias = bias; g.resid = resid; g.out = out;
@@ -441,6 +441,7 @@ int launch_variant(int variant, int epi, const CUtensorMap& ta, const CUtensorMa
     case CACO_GEMM_CG1_N256: return launch_epi<1, 256, 3, 8>(epi, ta, tb, g, max_ctas, stream);
     case CACO_GEMM_CG1_N128: return launch_epi<1, 128, 5, 8>(epi, ta, tb, g, max_ctas, stream);
     case CACO_GEMM_CG2_N256: return launch_epi<2, 256, 5, 8>(epi, ta, tb, g, max_ctas, stream);
+    case CACO_GEMM_CG2_N256_E16: return launch_epi<2, 256, 4, 16>(epi, ta, tb, g, max_ctas, stream);
   }
   return CACO_ERR_ARG;
 }

@@ -37,6 +37,7 @@ extern "C" {
 #define CACO_GEMM_CG1_N256 1  /* one CTA per 128x256 tile, tcgen05.mma.cta_group::1 */
 #define CACO_GEMM_CG1_N128 2  /* one CTA per 128x128 tile */
 #define CACO_GEMM_CG2_N256 3  /* CTA pair per 256x256 tile, tcgen05.mma.cta_group::2 */
+#define CACO_GEMM_CG2_N256_E16 4 /* same, 16 epilogue warps / 4 smem stages (activation-heavy epilogues) */
 
 /* Library/version probe; also reports the compute capability the kernels were built for (100). */
 int caco_version(void);

@@ -21,7 +21,8 @@ SHAPES = [  # (name, M, N, K, epi)
     ("t_fc1", 8192, 3072, 768, L.EPI_BIAS_GELU_F16),
     ("t_fc2", 8192, 768, 3072, L.EPI_BIAS_RESID_F32),
 ]
-VARIANTS = {"cg1_n256": L.GEMM_CG1_N256, "cg1_n128": L.GEMM_CG1_N128, "cg2_n256": L.GEMM_CG2_N256}
+VARIANTS = {"cg1_n256": L.GEMM_CG1_N256, "cg1_n128": L.GEMM_CG1_N128, "cg2_n256": L.GEMM_CG2_N256,
+            "cg2_e16": L.GEMM_CG2_N256_E16}
 
 
 def main():

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 from cacophony_b200 import _lib as L
 from cacophony_b200 import ops
 
-VARIANTS = {"cg1_n256": L.GEMM_CG1_N256, "cg1_n128": L.GEMM_CG1_N128, "cg2_n256": L.GEMM_CG2_N256}
+VARIANTS = {"cg1_n256": L.GEMM_CG1_N256, "cg1_n128": L.GEMM_CG1_N128, "cg2_n256": L.GEMM_CG2_N256,
+            "cg2_e16": L.GEMM_CG2_N256_E16}
 
 
 def _ref(a, w, bias, epi, resid):
