@@ -29,10 +29,10 @@ def gather_embeddings(a_local: torch.Tensor, t_local: torch.Tensor, group: Optio
         return a_local, t_local
     world = dist.get_world_size(group)
     send = torch.stack([a_local, t_local], dim=1).contiguous()                 # [B, 2, D]
-    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
     B, _, D = send.shape
-    return recv[:, :, 0, :].reshape(world * B, D), recv[:, :, 1, :].reshape(world * B, D)
+    recv = torch.empty((world * B, 2, D), dtype=send.dtype, device=send.device)      # rank-major concatenation
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:, 0, :].contiguous(), recv[:, 1, :].contiguous()
 
 
 def sharded_contrastive_logits(model, a_local: torch.Tensor, t_local: torch.Tensor,
