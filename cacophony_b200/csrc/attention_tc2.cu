@@ -1,0 +1,384 @@
+// K3a, persistent version — audio self-attention (mae.py:69-74,89-92), head_dim 96, one CTA per SM.
+//
+// A work item is 256 queries (two 128-row tiles A and B) of one (clip, head); every CTA walks a static list of items and
+// the whole thing is one flat software pipeline over (item, 64-key block) pairs, so nothing is set up or torn down between
+// items: the TMA producer is already loading the next item's Q (double-buffered) and K/V (3-stage rings) while the current
+// item's last blocks are in the softmax warps, and the tensor core computes the next item's first scores during the
+// current item's epilogue.
+//   warp 0      TMA producer + per-item key-mask bias (3-D tensor maps over qkv[clip][token][3*768], OOB rows = 0)
+//   warp 1      tcgen05.mma issuer: S_X(g) = Q_X K_g^T (M128 N64 K96, SW128 + SW64 K-major tiles), O_X += P_X(g) V_g
+//               (M128 N96 K64, V MN-major), X in {A, B}; S double-buffered per tile in tensor memory
+//   warps 2-5   softmax warpgroup A, warps 6-9 softmax warpgroup B: thread = query row, base-2 online softmax in fp32 with
+//               lazy rescaling (threshold 2^8), P -> fp16 -> 128B-swizzled smem; per-item epilogue O/l -> fp16 -> HBM
+// K_g/V_g are fetched once for 256 queries (half the L2->SM traffic of the one-tile kernel).
+// Tensor memory: S_A0 S_A1 S_B0 S_B1 (4 x 64 columns) + O_A O_B (2 x 96) = 448 of 512 columns.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "caco_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace caco {
+
+namespace t2 {
+constexpr int BM = 128, BN = 64, DH = 96, NST = 3;
+constexpr uint32_t Q_TILE = 24576;                 // 16 KB SW128 (cols 0..63) + 8 KB SW64 (cols 64..95)
+constexpr uint32_t OFF_Q = 0;                      // [buf 2][tile 2] x Q_TILE
+constexpr uint32_t OFF_K0 = 98304;                 // NST x 8192
+constexpr uint32_t OFF_K1 = OFF_K0 + NST * 8192;   // NST x 4096
+constexpr uint32_t OFF_V = OFF_K1 + NST * 4096;    // NST x 16384 (two 64-column blocks, 8192 B apart)
+constexpr uint32_t OFF_P = OFF_V + NST * 16384;    // [tile 2] x 16384
+constexpr uint32_t OFF_BAR = OFF_P + 2 * 16384;    // 256 B of mbarriers + tmem slot
+constexpr uint32_t OFF_BIAS = OFF_BAR + 256;       // [buf 2] x max_keys floats
+constexpr uint32_t K_BYTES = 12288, V_BYTES = 16384;
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_COLS = 512;
+constexpr float RESCALE_T = 8.0f;
+// barrier byte offsets inside the barrier block
+constexpr uint32_t B_QFULL = 0, B_ITEMDONE = 16, B_BIASFULL = 32, B_KFULL = 48, B_KEMPTY = 72, B_VFULL = 96, B_VEMPTY = 120,
+                   B_SFULL = 144 /* [tile][buf] */, B_SEMPTY = 176, B_PFULL = 208, B_PVDONE = 224, B_TMEMSLOT = 240;
+}  // namespace t2
+
+struct Attn2Args {
+  const float* mask;
+  __half* out;
+  int S, H, B;
+  int n_items;      // B * H * qpairs
+  int qpairs;       // ceil(S / 256)
+  int n_blocks;     // ceil(S / 64)
+  int max_keys;     // n_blocks * 64
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(320, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
+                     const __grid_constant__ CUtensorMap map_kv0, const __grid_constant__ CUtensorMap map_k1, const Attn2Args a) {
+  using namespace t2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR;
+  float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = a.H * DH, nb = a.n_blocks;
+  const int n_local = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
+  const int total = n_local * nb;                                                             // flat block count
+
+  if (tid == 0) {
+    if ((sb & 1023u) != 0) __trap();
+    tma_prefetch_desc(&map_q0); tma_prefetch_desc(&map_q1); tma_prefetch_desc(&map_kv0); tma_prefetch_desc(&map_k1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar + B_QFULL + 8 * i, 1);
+      mbar_init(bar + B_ITEMDONE + 8 * i, 8);
+      mbar_init(bar + B_BIASFULL + 8 * i, 1);
+      mbar_init(bar + B_PFULL + 8 * i, 4);
+      mbar_init(bar + B_PVDONE + 8 * i, 1);
+    }
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(bar + B_KFULL + 8 * i, 1); mbar_init(bar + B_KEMPTY + 8 * i, 1);
+      mbar_init(bar + B_VFULL + 8 * i, 1); mbar_init(bar + B_VEMPTY + 8 * i, 1);
+    }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar + B_SFULL + 8 * i, 1); mbar_init(bar + B_SEMPTY + 8 * i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(bar + B_TMEMSLOT, TM_COLS);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + B_TMEMSLOT);
+
+  auto decode = [&](int it, int& b, int& h, int& q0) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    const int qp = item % a.qpairs;
+    const int bh = item / a.qpairs;
+    h = bh % a.H;
+    b = bh / a.H;
+    q0 = qp * 2 * BM;
+  };
+
+  if (warp == 0) {
+    // ================================================================ producer
+    for (int it = 0; it < n_local; ++it) {
+      int b, h, q0;
+      decode(it, b, h, q0);
+      const int ib = it & 1;
+      if (it >= 2) mbar_wait(bar + B_ITEMDONE + 8 * ib, ((it >> 1) + 1) & 1);     // Q and bias buffers of item it-2 are free
+      if (lane == 0) {
+        const uint32_t qf = bar + B_QFULL + 8 * ib;
+        mbar_expect_tx(qf, 2 * Q_TILE);
+        for (int x = 0; x < 2; ++x) {
+          const uint32_t dst = sb + OFF_Q + (ib * 2 + x) * Q_TILE;
+          tma_load_3d(dst, &map_q0, qf, h * DH, q0 + x * BM, b);
+          tma_load_3d(dst + 16384, &map_q1, qf, h * DH + 64, q0 + x * BM, b);
+        }
+      }
+      // additive key bias of this clip: 0 = live key, -inf = masked key or padding past S
+      for (int j = lane; j < a.max_keys; j += 32)
+        s_bias[ib * a.max_keys + j] = (j < a.S && __ldg(a.mask + (size_t)b * a.S + j) != 0.0f) ? 0.0f : -INFINITY;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + B_BIASFULL + 8 * ib);
+      for (int j = 0; j < nb; ++j) {
+        const int g = it * nb + j, st = g % NST;
+        const uint32_t ph = ((g / NST) + 1) & 1;
+        if (g >= NST) mbar_wait(bar + B_KEMPTY + 8 * st, ph);
+        if (lane == 0) {
+          const uint32_t kf = bar + B_KFULL + 8 * st;
+          mbar_expect_tx(kf, K_BYTES);
+          tma_load_3d(sb + OFF_K0 + st * 8192, &map_kv0, kf, D + h * DH, j * BN, b);
+          tma_load_3d(sb + OFF_K1 + st * 4096, &map_k1, kf, D + h * DH + 64, j * BN, b);
+        }
+        if (g >= NST) mbar_wait(bar + B_VEMPTY + 8 * st, ph);
+        if (lane == 0) {
+          const uint32_t vf = bar + B_VFULL + 8 * st;
+          mbar_expect_tx(vf, V_BYTES);
+          tma_load_3d(sb + OFF_V + st * 16384, &map_kv0, vf, 2 * D + h * DH, j * BN, b);
+          tma_load_3d(sb + OFF_V + st * 16384 + 8192, &map_kv0, vf, 2 * D + h * DH + 64, j * BN, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc_qk = umma_idesc_f16(BM, BN);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(BM, DH, false, true);
+    auto issue_qk = [&](int g) {       // both tiles of flat block g (lane 0 only)
+      const int it = g / nb, ib = it & 1, st = g % NST, sbuf = g & 1;
+      const uint64_t k0 = umma_desc_kmajor_sw128(sb + OFF_K0 + st * 8192), k1 = umma_desc_kmajor_sw64(sb + OFF_K1 + st * 4096);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const uint32_t q = sb + OFF_Q + (ib * 2 + x) * Q_TILE;
+        const uint64_t a0 = umma_desc_kmajor_sw128(q), a1 = umma_desc_kmajor_sw64(q + 16384);
+        const uint32_t d = tmem_base + TM_S + (x * 2 + sbuf) * BN;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16<1>(d, a0 + 2 * ks, k0 + 2 * ks, idesc_qk, ks ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_f16<1>(d, a1 + 2 * ks, k1 + 2 * ks, idesc_qk, 1u);
+        umma_commit<1>(bar + B_SFULL + 8 * (x * 2 + sbuf));
+      }
+      umma_commit<1>(bar + B_KEMPTY + 8 * st);
+    };
+    auto wait_qk_inputs = [&](int g) {   // whole warp
+      const int it = g / nb;
+      if (g % nb == 0) mbar_wait(bar + B_QFULL + 8 * (it & 1), (it >> 1) & 1);
+      mbar_wait(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1);
+      if (g >= 2) {
+        const uint32_t ph = ((g >> 1) + 1) & 1;
+        mbar_wait(bar + B_SEMPTY + 8 * (0 + (g & 1)), ph);
+        mbar_wait(bar + B_SEMPTY + 8 * (2 + (g & 1)), ph);
+      }
+      tc_fence_after();
+    };
+    if (total > 0) {
+      wait_qk_inputs(0);
+      if (lane == 0) issue_qk(0);
+      __syncwarp();
+    }
+    for (int g = 0; g < total; ++g) {
+      if (g + 1 < total) {
+        wait_qk_inputs(g + 1);
+        if (lane == 0) issue_qk(g + 1);
+        __syncwarp();
+      }
+      const int st = g % NST;
+      const uint32_t acc0 = (g % nb) ? 1u : 0u;
+      mbar_wait(bar + B_VFULL + 8 * st, (g / NST) & 1);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(bar + B_PFULL + 8 * x, g & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t pa = umma_desc_kmajor_sw128(sb + OFF_P + x * 16384);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t vb = umma_desc_mnmajor_sw128(sb + OFF_V + st * 16384 + ks * 2048, 8192);
+            umma_f16<1>(tmem_base + TM_O + x * DH, pa + 2 * ks, vb, idesc_pv, (acc0 | (uint32_t)ks) ? 1u : 0u);
+          }
+          umma_commit<1>(bar + B_PVDONE + 8 * x);
+          if (x == 1) umma_commit<1>(bar + B_VEMPTY + 8 * st);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================ softmax warpgroups (thread = query row)
+    const int x = (warp - 2) >> 2;                  // tile: 0 = A, 1 = B
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (uint32_t(quarter * 32) << 16);
+    uint8_t* p_row = smem + OFF_P + x * 16384 + row * 128;
+    const uint32_t b_sfull = bar + B_SFULL + 8 * (x * 2), b_sempty = bar + B_SEMPTY + 8 * (x * 2);
+    const uint32_t b_pfull = bar + B_PFULL + 8 * x, b_pvdone = bar + B_PVDONE + 8 * x;
+    float m_ref = -INFINITY, l_run = 0.f;
+    int b = 0, h = 0, q0 = 0;
+    for (int g = 0; g < total; ++g) {
+      const int it = g / nb, j = g - it * nb, ib = it & 1, sbuf = g & 1;
+      if (j == 0) {
+        decode(it, b, h, q0);
+        mbar_wait(bar + B_BIASFULL + 8 * ib, (it >> 1) & 1);
+        m_ref = -INFINITY;
+        l_run = 0.f;
+      }
+      mbar_wait(b_sfull + 8 * sbuf, (g >> 1) & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(t_lane + TM_S + (x * 2 + sbuf) * BN, v0);
+      tmem_ld_32x32(t_lane + TM_S + (x * 2 + sbuf) * BN + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_sempty + 8 * sbuf);
+      float t[64];
+      float mx = -INFINITY;
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + ib * a.max_keys + j * BN);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 bb = bias4[c];
+        const uint32_t* src = (c < 8) ? &v0[4 * c] : &v1[4 * (c - 8)];
+        t[4 * c + 0] = fmaf(__uint_as_float(src[0]), a.scale_log2, bb.x);
+        t[4 * c + 1] = fmaf(__uint_as_float(src[1]), a.scale_log2, bb.y);
+        t[4 * c + 2] = fmaf(__uint_as_float(src[2]), a.scale_log2, bb.z);
+        t[4 * c + 3] = fmaf(__uint_as_float(src[3]), a.scale_log2, bb.w);
+        mx = fmaxf(mx, fmaxf(fmaxf(t[4 * c], t[4 * c + 1]), fmaxf(t[4 * c + 2], t[4 * c + 3])));
+      }
+      const bool need = mx > m_ref + RESCALE_T;               // m_ref == -inf: true iff this block has a live key
+      if (__any_sync(0xffffffffu, need)) {
+        const float factor = need ? exp2f(m_ref - mx) : 1.0f;
+        if (j > 0) {
+          mbar_wait(b_pvdone, (g - 1) & 1);                   // O_X holds every P V of this item issued so far
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < DH / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st_32x16(t_lane + TM_O + x * DH + c * 16, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        l_run *= factor;
+        if (need) m_ref = mx;
+      }
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      uint32_t ph[32];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float p0 = fast_exp2(t[2 * c] - m_use), p1 = fast_exp2(t[2 * c + 1] - m_use);
+        sum += p0 + p1;
+        __half2 hh = __floats2half2_rn(p0, p1);
+        ph[c] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      l_run += sum;
+      if (g > 0) mbar_wait(b_pvdone, (g - 1) & 1);            // P_X buffer is free once P_X(g-1) V(g-1) retired
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        uint4 u = make_uint4(ph[4 * cc], ph[4 * cc + 1], ph[4 * cc + 2], ph[4 * cc + 3]);
+        *reinterpret_cast<uint4*>(p_row + ((cc ^ (row & 7)) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull);
+      if (j == nb - 1) {
+        // ---- item epilogue: O / l -> fp16 (the next item's first P V cannot be issued before this warp signals P again)
+        mbar_wait(b_pvdone, g & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
+        const int q = q0 + x * BM + row;
+        __half* dst = a.out + ((size_t)b * a.S + q) * D + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o);
+          tmem_ld_wait();
+          if (q < a.S) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+              pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + B_ITEMDONE + 8 * ib);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled2 encode_fn2() {
+  static PFN_encodeTiled2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled2>(p);
+  }
+  return fn;
+}
+static int make_map3b(CUtensorMap* m, const void* base, int batch, int seq, int ld, int box_cols, int box_rows, bool sw128) {
+  PFN_encodeTiled2 enc = encode_fn2();
+  if (!enc) return CACO_ERR_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)seq, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)seq};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
+}
+
+int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
+                        cudaStream_t stream) {
+  using namespace t2;
+  if (!qkv || !mask || !out || batch <= 0 || seq <= 0 || heads <= 0 || dh != DH) return CACO_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return CACO_ERR_ALIGN;
+  Attn2Args a;
+  a.mask = mask; a.out = (__half*)out; a.S = seq; a.H = heads; a.B = batch;
+  a.qpairs = (seq + 2 * BM - 1) / (2 * BM);
+  a.n_items = batch * heads * a.qpairs;
+  a.n_blocks = (seq + BN - 1) / BN;
+  a.max_keys = a.n_blocks * BN;
+  a.scale_log2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+  const size_t smem = OFF_BIAS + 2 * (size_t)a.max_keys * 4;
+  if (smem > 232448) return CACO_ERR_ARG;     // seq <= 1536
+  const int ld = 3 * heads * dh;
+  CUtensorMap mq0, mq1, mkv0, mk1;
+  int rc;
+  if ((rc = make_map3b(&mq0, qkv, batch, seq, ld, 64, BM, true))) return rc;
+  if ((rc = make_map3b(&mq1, qkv, batch, seq, ld, 32, BM, false))) return rc;
+  if ((rc = make_map3b(&mkv0, qkv, batch, seq, ld, 64, BN, true))) return rc;
+  if ((rc = make_map3b(&mk1, qkv, batch, seq, ld, 32, BN, false))) return rc;
+  static size_t cur = 0;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return (int)e;
+    cur = smem;
+  }
+  int grid = num_sms();
+  if (grid > a.n_items) grid = a.n_items;
+  attention_tc2_kernel<<<grid, 320, smem, stream>>>(mq0, mq1, mkv0, mk1, a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace caco
