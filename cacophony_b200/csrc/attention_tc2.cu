@@ -162,15 +162,18 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
       }
       umma_commit<1>(bar + B_KEMPTY + 8 * st);
     };
-    auto wait_qk_inputs = [&](int g) {   // whole warp
+    auto wait_qk_inputs = [&](int g) {   // whole warp; the (already complete in steady state) barriers are probed together
       const int it = g / nb;
-      if (g % nb == 0) mbar_wait(bar + B_QFULL + 8 * (it & 1), (it >> 1) & 1);
-      mbar_wait(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1);
-      if (g >= 2) {
-        const uint32_t ph = ((g >> 1) + 1) & 1;
-        mbar_wait(bar + B_SEMPTY + 8 * (0 + (g & 1)), ph);
-        mbar_wait(bar + B_SEMPTY + 8 * (2 + (g & 1)), ph);
-      }
+      const bool need_q = (g % nb == 0), need_s = (g >= 2);
+      const uint32_t bq = bar + B_QFULL + 8 * (it & 1), pq = (it >> 1) & 1;
+      const uint32_t bk = bar + B_KFULL + 8 * (g % NST), pk = (g / NST) & 1;
+      const uint32_t bs0 = bar + B_SEMPTY + 8 * (0 + (g & 1)), bs1 = bar + B_SEMPTY + 8 * (2 + (g & 1)), ps = ((g >> 1) + 1) & 1;
+      bool ok;
+      do {
+        ok = mbar_try_wait(bk, pk);
+        if (need_q) ok = mbar_try_wait(bq, pq) && ok;
+        if (need_s) { const bool o0 = mbar_try_wait(bs0, ps), o1 = mbar_try_wait(bs1, ps); ok = ok && o0 && o1; }
+      } while (!ok);
       tc_fence_after();
     };
     if (total > 0) {
@@ -252,13 +255,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
           mbar_wait(b_pvdone, (g - 1) & 1);                   // O_X holds every P V of this item issued so far
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < DH / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o);
+          for (int hc = 0; hc < 2; ++hc) {                    // two batches of 48 columns keep the register peak down
+            uint32_t o[3][16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tmem_ld_32x16(t_lane + TM_O + x * DH + (hc * 3 + c) * 16, o[c]);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st_32x16(t_lane + TM_O + x * DH + c * 16, o);
+            for (int c = 0; c < 3; ++c) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[c][i] = __float_as_uint(__uint_as_float(o[c][i]) * factor);
+              tmem_st_32x16(t_lane + TM_O + x * DH + (hc * 3 + c) * 16, o[c]);
+            }
           }
           tmem_st_wait();
           tc_fence_before();
@@ -293,23 +300,26 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
         const int q = q0 + x * BM + row;
         __half* dst = a.out + ((size_t)b * a.S + q) * D + h * DH;
+        // all six TMEM loads are issued before the single wait: a tcgen05.ld issued while the tensor pipe is busy with the
+        // next item's Q K^T takes ~900 cycles, so six dependent load/wait pairs cost 5 k cycles per item (measured)
+        uint32_t o[DH / 16][16];
 #pragma unroll
-        for (int c = 0; c < DH / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o);
-          tmem_ld_wait();
-          if (q < a.S) {
+        for (int c = 0; c < DH / 16; ++c) tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        if (q < a.S) {
+#pragma unroll
+          for (int c = 0; c < DH / 16; ++c) {
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+              __half2 hh = __floats2half2_rn(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
               pk[i] = *reinterpret_cast<uint32_t*>(&hh);
             }
             *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dst + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
-        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + B_ITEMDONE + 8 * ib);
       }
