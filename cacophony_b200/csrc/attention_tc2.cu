@@ -5,7 +5,8 @@
 // items: the TMA producer is already loading the next item's Q (double-buffered) and K/V (3-stage rings) while the current
 // item's last blocks are in the softmax warps, and the tensor core computes the next item's first scores during the
 // current item's epilogue.
-//   warp 0      TMA producer + per-item key-mask bias (3-D tensor maps over qkv[clip][token][3*768], OOB rows = 0)
+//   warps 0, 10, 11  TMA producers: K ring, V ring, per-item Q + key-mask bias (3-D tensor maps over
+//               qkv[clip][token][3*768], OOB rows = 0); three independent in-order streams
 //   warp 1      tcgen05.mma issuer: S_X(g) = Q_X K_g^T (M128 N64 K96, SW128 + SW64 K-major tiles), O_X += P_X(g) V_g
 //               (M128 N96 K64, V MN-major), X in {A, B}; S double-buffered per tile in tensor memory
 //   warps 2-5   softmax warpgroup A, warps 6-9 softmax warpgroup B: thread = query row, base-2 online softmax in fp32 with
@@ -53,7 +54,7 @@ struct Attn2Args {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                      const __grid_constant__ CUtensorMap map_kv0, const __grid_constant__ CUtensorMap map_k1, const Attn2Args a) {
   using namespace t2;
@@ -102,7 +103,43 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
   };
 
   if (warp == 0) {
-    // ================================================================ producer
+    // ================================================================ K producer (flat over all blocks of all items)
+    // K_g's slot frees when Q K_{g-3}^T (both tiles) retires; separate warps feed V and Q so that no ring waits behind
+    // another ring's slot (a single in-order producer exposed the TMA latency on every block: measured 3.3 k cycles/block)
+    for (int it = 0; it < n_local; ++it) {
+      int b, h, q0;
+      decode(it, b, h, q0);
+      for (int j = 0; j < nb; ++j) {
+        const int g = it * nb + j, st = g % NST;
+        if (g >= NST) mbar_wait(bar + B_KEMPTY + 8 * st, ((g / NST) + 1) & 1);
+        if (lane == 0) {
+          const uint32_t kf = bar + B_KFULL + 8 * st;
+          mbar_expect_tx(kf, K_BYTES);
+          tma_load_3d(sb + OFF_K0 + st * 8192, &map_kv0, kf, D + h * DH, j * BN, b);
+          tma_load_3d(sb + OFF_K1 + st * 4096, &map_k1, kf, D + h * DH + 64, j * BN, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 10) {
+    // ================================================================ V producer
+    for (int it = 0; it < n_local; ++it) {
+      int b, h, q0;
+      decode(it, b, h, q0);
+      for (int j = 0; j < nb; ++j) {
+        const int g = it * nb + j, st = g % NST;
+        if (g >= NST) mbar_wait(bar + B_VEMPTY + 8 * st, ((g / NST) + 1) & 1);
+        if (lane == 0) {
+          const uint32_t vf = bar + B_VFULL + 8 * st;
+          mbar_expect_tx(vf, V_BYTES);
+          tma_load_3d(sb + OFF_V + st * 16384, &map_kv0, vf, 2 * D + h * DH, j * BN, b);
+          tma_load_3d(sb + OFF_V + st * 16384 + 8192, &map_kv0, vf, 2 * D + h * DH + 64, j * BN, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 11) {
+    // ================================================================ Q + key-mask-bias producer (per item, double-buffered)
     for (int it = 0; it < n_local; ++it) {
       int b, h, q0;
       decode(it, b, h, q0);
@@ -122,25 +159,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         s_bias[ib * a.max_keys + j] = (j < a.S && __ldg(a.mask + (size_t)b * a.S + j) != 0.0f) ? 0.0f : -INFINITY;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + B_BIASFULL + 8 * ib);
-      for (int j = 0; j < nb; ++j) {
-        const int g = it * nb + j, st = g % NST;
-        const uint32_t ph = ((g / NST) + 1) & 1;
-        if (g >= NST) mbar_wait(bar + B_KEMPTY + 8 * st, ph);
-        if (lane == 0) {
-          const uint32_t kf = bar + B_KFULL + 8 * st;
-          mbar_expect_tx(kf, K_BYTES);
-          tma_load_3d(sb + OFF_K0 + st * 8192, &map_kv0, kf, D + h * DH, j * BN, b);
-          tma_load_3d(sb + OFF_K1 + st * 4096, &map_k1, kf, D + h * DH + 64, j * BN, b);
-        }
-        if (g >= NST) mbar_wait(bar + B_VEMPTY + 8 * st, ph);
-        if (lane == 0) {
-          const uint32_t vf = bar + B_VFULL + 8 * st;
-          mbar_expect_tx(vf, V_BYTES);
-          tma_load_3d(sb + OFF_V + st * 16384, &map_kv0, vf, 2 * D + h * DH, j * BN, b);
-          tma_load_3d(sb + OFF_V + st * 16384 + 8192, &map_kv0, vf, 2 * D + h * DH + 64, j * BN, b);
-        }
-        __syncwarp();
-      }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -207,7 +225,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ================================================================ softmax warpgroups (thread = query row)
     const int x = (warp - 2) >> 2;                  // tile: 0 = A, 1 = B
     const int quarter = warp & 3;
@@ -386,7 +404,7 @@ int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch
   }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;
-  attention_tc2_kernel<<<grid, 320, smem, stream>>>(mq0, mq1, mkv0, mk1, a);
+  attention_tc2_kernel<<<grid, 384, smem, stream>>>(mq0, mq1, mkv0, mk1, a);
   count_launch();
   return (int)cudaGetLastError();
 }
