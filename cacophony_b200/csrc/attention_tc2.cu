@@ -43,6 +43,13 @@ constexpr uint32_t B_QFULL = 0, B_ITEMDONE = 16, B_BIASFULL = 32, B_KFULL = 48, 
                    B_SFULL = 144 /* [tile][buf] */, B_SEMPTY = 176, B_PFULL = 208, B_PVDONE = 224, B_TMEMSLOT = 240;
 }  // namespace t2
 
+// optional timeline trace of CTA 0 (debug/profiling aid): [role 2][block 64][event 8] clock64 stamps
+__device__ long long* g_attn_trace = nullptr;
+#define TC2_STAMP(role, blk, ev)                                                              \
+  do {                                                                                        \
+    if (trace != nullptr && (blk) < 64) trace[((role) * 64 + (blk)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
 struct Attn2Args {
   const float* mask;
   __half* out;
@@ -66,6 +73,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
   const int D = a.H * DH, nb = a.n_blocks;
   const int n_local = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
   const int total = n_local * nb;                                                             // flat block count
+  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2)) ? g_attn_trace : nullptr;
 
   if (tid == 0) {
     if ((sb & 1023u) != 0) __trap();
@@ -200,10 +208,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
       __syncwarp();
     }
     for (int g = 0; g < total; ++g) {
+      TC2_STAMP(0, g, 0);
       if (g + 1 < total) {
         wait_qk_inputs(g + 1);
+        TC2_STAMP(0, g, 1);
         if (lane == 0) issue_qk(g + 1);
         __syncwarp();
+        TC2_STAMP(0, g, 2);
       }
       const int st = g % NST;
       const uint32_t acc0 = (g % nb) ? 1u : 0u;
@@ -211,6 +222,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         mbar_wait(bar + B_PFULL + 8 * x, g & 1);
+        TC2_STAMP(0, g, 3 + 2 * x);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t pa = umma_desc_kmajor_sw128(sb + OFF_P + x * 16384);
@@ -223,6 +235,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
           if (x == 1) umma_commit<1>(bar + B_VEMPTY + 8 * st);
         }
         __syncwarp();
+        TC2_STAMP(0, g, 4 + 2 * x);
       }
     }
   } else if (warp < 10) {
@@ -244,12 +257,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         m_ref = -INFINITY;
         l_run = 0.f;
       }
+      TC2_STAMP(1, g, 0);
       mbar_wait(b_sfull + 8 * sbuf, (g >> 1) & 1);
+      TC2_STAMP(1, g, 1);
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(t_lane + TM_S + (x * 2 + sbuf) * BN, v0);
       tmem_ld_32x32(t_lane + TM_S + (x * 2 + sbuf) * BN + 32, v1);
       tmem_ld_wait();
+      TC2_STAMP(1, g, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_sempty + 8 * sbuf);
@@ -302,6 +318,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
         ph[c] = *reinterpret_cast<uint32_t*>(&hh);
       }
       l_run += sum;
+      TC2_STAMP(1, g, 3);
       if (g > 0) mbar_wait(b_pvdone, (g - 1) & 1);            // P_X buffer is free once P_X(g-1) V(g-1) retired
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
@@ -311,9 +328,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_pfull);
+      TC2_STAMP(1, g, 4);
       if (j == nb - 1) {
         // ---- item epilogue: O / l -> fp16 (the next item's first P V cannot be issued before this warp signals P again)
         mbar_wait(b_pvdone, g & 1);
+        TC2_STAMP(1, g, 5);
         tc_fence_after();
         const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
         const int q = q0 + x * BM + row;
@@ -324,6 +343,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
 #pragma unroll
         for (int c = 0; c < DH / 16; ++c) tmem_ld_32x16(t_lane + TM_O + x * DH + c * 16, o[c]);
         tmem_ld_wait();
+        TC2_STAMP(1, g, 6);
         tc_fence_before();
         if (q < a.S) {
 #pragma unroll
@@ -338,6 +358,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_co
             *reinterpret_cast<uint4*>(dst + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
+        TC2_STAMP(1, g, 7);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + B_ITEMDONE + 8 * ib);
       }
@@ -410,3 +431,9 @@ int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch
 }
 
 }  // namespace caco
+
+// debug aid: pass a device buffer of 2*64*8 int64 (or NULL to disable); CTA 0 stamps clock64 at pipeline events
+extern "C" int caco_attn_trace(void* dev_buf) {
+  long long* p = (long long*)dev_buf;
+  return (int)cudaMemcpyToSymbol(caco::g_attn_trace, &p, sizeof(p));
+}
