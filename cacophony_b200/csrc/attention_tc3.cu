@@ -59,7 +59,8 @@ struct Attn3Args {
 };
 
 __global__ void __launch_bounds__(384, 1)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_constant__ CUtensorMap map_32, const Attn3Args a) {
+attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_constant__ CUtensorMap map_32,
+                     const __grid_constant__ CUtensorMap map_o64, const __grid_constant__ CUtensorMap map_o32, const Attn3Args a) {
   using namespace t3;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -74,7 +75,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
 
   if (tid == 0) {
     if ((sb & 1023u) != 0) __trap();
-    tma_prefetch_desc(&map_64); tma_prefetch_desc(&map_32);
+    tma_prefetch_desc(&map_64); tma_prefetch_desc(&map_32); tma_prefetch_desc(&map_o64); tma_prefetch_desc(&map_o32);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar + B_QFULL + 8 * i, 1);
       mbar_init(bar + B_ITEMDONE + 8 * i, 8);
@@ -248,19 +249,24 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
       mbar_wait(b_sfull, g & 1);                              // S_x(g) complete => every earlier MMA (incl. P_x V of g-1) retired
       TC3_STAMP(1, g, 1);
       tc_fence_after();
-      // ---- pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling)
+      // ---- pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling).  tcgen05.ld is slow while
+      // the tensor pipe is busy (several hundred cycles, measured), so the next chunk is always in flight during the math.
+      uint32_t va[32], vb[32];
       float mx = -INFINITY;
+      tmem_ld_32x32(t_s, va);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
         tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? vb : va;
+        uint32_t* nxt = (c & 1) ? va : vb;
+        if (c + 1 < BN / 32) tmem_ld_32x32(t_s + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(nxt));
+        else tmem_ld_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(nxt));      // first chunk of pass 2
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) + bias[c * 32 + i]);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]) + bias[c * 32 + i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
         }
       }
       mx *= a.scale_log2;                                     // -inf stays -inf
@@ -270,6 +276,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
       if (__any_sync(0xffffffffu, need)) {
         const float factor = need ? exp2f(m_ref - mx) : 1.0f;
         if (j > 0) {
+          tmem_ld_wait();                                     // the pass-2 prefetch shares the wait group: drain it first
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {
             uint32_t o[3][16];
@@ -288,25 +295,29 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
         if (need) m_ref = mx;
       }
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-      // ---- pass 2: p = exp2(s*scale - m), row sum, pack to fp16 and write P over the S columns already consumed
+      // ---- pass 2: p = exp2(s*scale - m), row sum, pack to fp16 and write P over the S columns already consumed.
+      // BN/32 is even, so pass 2 starts in buffer va (prefetched above) and alternates like pass 1.
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c * 32, v);
         tmem_ld_wait();
+        uint32_t* cur = (c & 1) ? vb : va;
+        uint32_t* nxt = (c & 1) ? va : vb;
+        if (c + 1 < BN / 32) tmem_ld_32x32(t_s + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(nxt));
         uint32_t ph[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float t0 = fmaf(__uint_as_float(v[2 * i]), a.scale_log2, neg_m);
-          float t1 = fmaf(__uint_as_float(v[2 * i + 1]), a.scale_log2, neg_m);
+          float t0 = fmaf(__uint_as_float(cur[2 * i]), a.scale_log2, neg_m);
+          float t1 = fmaf(__uint_as_float(cur[2 * i + 1]), a.scale_log2, neg_m);
           if (masked) { t0 += bias[c * 32 + 2 * i]; t1 += bias[c * 32 + 2 * i + 1]; }
           const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
           sum += p0 + p1;
           __half2 hh = __floats2half2_rn(p0, p1);
           ph[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        tmem_st_32x16(t_s + c * 16, ph);                      // keys 32c..32c+31 -> columns 16c..16c+15 (<= columns read so far)
+        // keys 32c..32c+31 -> columns 16c..16c+15: never ahead of the columns already read; chunk c+1 (columns 32c+32..)
+        // in flight is above them too
+        tmem_st_32x16(t_s + c * 16, ph);
       }
       l_run += sum;
       tmem_st_wait();
@@ -320,29 +331,45 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
         TC3_STAMP(1, g, 4);
         tc_fence_after();
         const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
-        const int q = q0 + x * BM + row;
-        __half* dst = a.out + ((size_t)b * a.S + q) * D + h * DH;
+        // O tile -> fp16 -> this item's (now dead) Q_x buffer in the swizzled layouts of the two output tensor maps ->
+        // one TMA store per warp (32 rows x 64 + 32 columns); rows past the clip's end are clipped by the hardware
+        uint8_t* stage = smem + OFF_Q + (ib * 2 + x) * Q_TILE;
+        uint8_t* r0 = stage + row * 128;
+        uint8_t* r1 = stage + 16384 + row * 64;
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           uint32_t o[3][16];
 #pragma unroll
           for (int c = 0; c < 3; ++c) tmem_ld_32x16(t_o + (hc * 3 + c) * 16, o[c]);
           tmem_ld_wait();
-          if (q < a.S) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              uint32_t pk[8];
+          for (int c = 0; c < 3; ++c) {
+            uint32_t pk[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __half2 hh = __floats2half2_rn(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
-                pk[i] = *reinterpret_cast<uint32_t*>(&hh);
-              }
-              *reinterpret_cast<uint4*>(dst + (hc * 3 + c) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(dst + (hc * 3 + c) * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            for (int i = 0; i < 8; ++i) {
+              __half2 hh = __floats2half2_rn(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
+              pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            const int col16 = (hc * 3 + c) * 2;                // index of the first of two 16-byte chunks (8 fp16 each)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int ch = col16 + k;                        // 0..11
+              const uint4 u = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+              if (ch < 8) *reinterpret_cast<uint4*>(r0 + ((ch ^ (row & 7)) << 4)) = u;                       // SWIZZLE_128B
+              else *reinterpret_cast<uint4*>(r1 + (((ch - 8) ^ ((row >> 1) & 3)) << 4)) = u;                 // SWIZZLE_64B
             }
           }
         }
         tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int qrow = q0 + x * BM + quarter * 32;
+          tma_store_3d(&map_o64, sb + OFF_Q + (ib * 2 + x) * Q_TILE + quarter * 32 * 128, h * DH, qrow, b);
+          tma_store_3d(&map_o32, sb + OFF_Q + (ib * 2 + x) * Q_TILE + 16384 + quarter * 32 * 64, h * DH + 64, qrow, b);
+          tma_store_commit();
+          tma_store_wait_read<0>();                            // smem may be refilled with the next-but-one item's Q
+        }
         TC3_STAMP(1, g, 5);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + B_ITEMDONE + 8 * ib);
@@ -396,10 +423,12 @@ int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch
   const size_t smem = OFF_BIAS + 2 * (size_t)a.max_keys * 4;
   if (smem > 232448 || a.n_blocks > 32) return CACO_ERR_ARG;
   const int ld = 3 * heads * dh;
-  CUtensorMap m64, m32;
+  CUtensorMap m64, m32, o64, o32;
   int rc;
   if ((rc = make_map3c(&m64, qkv, batch, seq, ld, 64, BM, true))) return rc;
   if ((rc = make_map3c(&m32, qkv, batch, seq, ld, 32, BM, false))) return rc;
+  if ((rc = make_map3c(&o64, out, batch, seq, heads * dh, 64, 32, true))) return rc;      // per-warp store boxes: 32 rows
+  if ((rc = make_map3c(&o32, out, batch, seq, heads * dh, 32, 32, false))) return rc;
   static size_t cur = 0;
   if (smem > cur) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -408,7 +437,7 @@ int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch
   }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;
-  attention_tc3_kernel<<<grid, 384, smem, stream>>>(m64, m32, a);
+  attention_tc3_kernel<<<grid, 384, smem, stream>>>(m64, m32, o64, o32, a);
   count_launch();
   return (int)cudaGetLastError();
 }
