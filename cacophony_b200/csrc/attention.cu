@@ -5,8 +5,8 @@
 //   fp32 softmax over keys, P·V, heads concatenated.  Flash-style: one CTA = 64 queries of one (clip, head),
 //   K/V streamed in 64-key tiles through a cp.async double buffer, scores never leave the SM
 //   (materialised they would be H*S^2*4 = 8 MB per clip per layer).
-// attention_text: causal + key-padding attention of the RoBERTa tower (roberta.py:86-102, mask :297-310),
-//   T <= 256, 12 heads x 64: far too small for tensor-core tiles, done per (caption, head) in fp32.
+// attention_text: causal + key-padding attention of the RoBERTa tower (roberta.py:86-102, mask :297-310), 12 heads x 64:
+//   the warp-MMA flash kernel with a causal predicate (key tiles past the diagonal are skipped).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -69,7 +69,7 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __half* src, int r
   }
 }
 
-template <int DH>
+template <int DH, bool CAUSAL = false>
 __global__ void __launch_bounds__(128)
 attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__ mask, __half* __restrict__ out, int S,
                        int H, float scale_log2) {
@@ -90,7 +90,8 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
   const __half* gV = base + 2 * D + h * DH;
   const float* gmask = mask + (size_t)b * S;
 
-  const int n_tiles = (S + AT_BN - 1) / AT_BN;
+  // causal (text tower, roberta.py:297-310): key tiles past this query tile's last row are never needed
+  const int n_tiles = CAUSAL ? min((S + AT_BN - 1) / AT_BN, (q0 + AT_BM - 1) / AT_BN + 1) : (S + AT_BN - 1) / AT_BN;
   load_tile<DH>(sQ, gQ, q0, S, ld, tid);
   load_tile<DH>(sK, gK, 0, S, ld, tid);
   load_tile<DH>(sV, gV, 0, S, ld, tid);
@@ -156,6 +157,13 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
       s[i][1] = s[i][1] * scale_log2 + b1;
       s[i][2] = s[i][2] * scale_log2 + b0;
       s[i][3] = s[i][3] * scale_log2 + b1;
+      if (CAUSAL) {                     // allowed(i, j) = j <= i  (on top of the key-padding bias)
+        const int col = t * AT_BN + c, r0 = q0 + warp * 16 + (lane >> 2);
+        if (col > r0) s[i][0] = -INFINITY;
+        if (col + 1 > r0) s[i][1] = -INFINITY;
+        if (col > r0 + 8) s[i][2] = -INFINITY;
+        if (col + 1 > r0 + 8) s[i][3] = -INFINITY;
+      }
       mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
     }
@@ -245,9 +253,10 @@ static int g_attn_impl = 0;   // 0 = auto, 1 = warp-level mma.sync kernel, 2 = t
 int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                     cudaStream_t stream) {
   if (!qkv || !mask || !out || batch <= 0 || seq <= 0 || heads <= 0) return CACO_ERR_ARG;
-  if (dh == 96 && g_attn_impl == 4 && seq <= 2304) return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
+  if (dh == 96 && (g_attn_impl == 0 || g_attn_impl == 4) && seq <= 2304)
+    return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
   if (dh == 96 && g_attn_impl != 1) {
-    if ((g_attn_impl == 0 || g_attn_impl == 3) && seq <= 1856) return attention_audio_tc2(qkv, mask, out, batch, seq, heads, dh, stream);
+    if (g_attn_impl != 2 && seq <= 1856) return attention_audio_tc2(qkv, mask, out, batch, seq, heads, dh, stream);
     if (seq <= 1728) return attention_audio_tc(qkv, mask, out, batch, seq, heads, dh, stream);
   }
   if ((heads * dh) % 8) return CACO_ERR_ARG;
@@ -270,96 +279,22 @@ int attention_audio(const void* qkv, const float* mask, void* out, int batch, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// text tower: one CTA per (caption, head); K/V of the head in shared memory (fp16, padded rows),
-// each warp owns query rows i = warp, warp+4, ...; lanes split the keys j <= i.
+// text tower (roberta.py:86-102, mask :297-310): the same kernel with head_dim 64 and the causal predicate
 // ------------------------------------------------------------------------------------------------
-constexpr int TX_MAXT = 256;
-constexpr int TX_LD = 66;  // 64 + 2 halfs: row stride 33 words -> conflict-free column walks
-
-__global__ void __launch_bounds__(128)
-attention_text_kernel(const __half* __restrict__ qkv, const float* __restrict__ key_mask, __half* __restrict__ out, int T,
-                      int H, float scale) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __half* sK = reinterpret_cast<__half*>(smem);
-  __half* sV = sK + T * TX_LD;
-  float* sBias = reinterpret_cast<float*>(sV + T * TX_LD);  // 264*T bytes in: 4-byte aligned
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int D = H * 64, ld = 3 * D;
-  const __half* base = qkv + (size_t)b * T * ld + h * 64;
-  for (int i = tid; i < T * 32; i += 128) {
-    const int r = i >> 5, c = (i & 31) * 2;
-    *reinterpret_cast<__half2*>(sK + r * TX_LD + c) = *reinterpret_cast<const __half2*>(base + (size_t)r * ld + D + c);
-    *reinterpret_cast<__half2*>(sV + r * TX_LD + c) = *reinterpret_cast<const __half2*>(base + (size_t)r * ld + 2 * D + c);
-  }
-  for (int i = tid; i < T; i += 128) sBias[i] = (key_mask[(size_t)b * T + i] != 0.0f) ? 0.0f : -INFINITY;
-  __syncthreads();
-
-  constexpr int MAXJ = TX_MAXT / 32;
-  for (int i = warp; i < T; i += 4) {
-    // q row broadcast to every lane
-    float2 q[32];
-    const __half2* gq = reinterpret_cast<const __half2*>(base + (size_t)i * ld);
-#pragma unroll
-    for (int c = 0; c < 32; ++c) q[c] = __half22float2(gq[c]);
-    float sc[MAXJ];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < MAXJ; ++jj) {
-      const int j = jj * 32 + lane;
-      float a = -INFINITY;
-      if (jj * 32 <= i && j <= i && j < T) {
-        const __half2* kr = reinterpret_cast<const __half2*>(sK + j * TX_LD);
-        float acc = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float2 kf = __half22float2(kr[c]);
-          acc = fmaf(q[c].x, kf.x, acc);
-          acc = fmaf(q[c].y, kf.y, acc);
-        }
-        a = acc * scale + sBias[j];
-      }
-      sc[jj] = a;
-      mx = fmaxf(mx, a);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < MAXJ; ++jj) {
-      sc[jj] = __expf(sc[jj] - mx);   // mx == -inf (row fully masked) -> NaN, as torch.softmax gives
-      sum += sc[jj];
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int jj = 0; jj < MAXJ; ++jj) {
-      if (jj * 32 <= i) {
-        const int jend = min(32, i + 1 - jj * 32);
-        for (int l = 0; l < jend; ++l) {
-          const float p = __shfl_sync(0xffffffffu, sc[jj], l);
-          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(sV + (jj * 32 + l) * TX_LD + lane * 2));
-          acc.x = fmaf(p, vf.x, acc.x);
-          acc.y = fmaf(p, vf.y, acc.y);
-        }
-      }
-    }
-    *reinterpret_cast<__half2*>(out + ((size_t)b * T + i) * D + h * 64 + lane * 2) = __floats2half2_rn(acc.x * inv, acc.y * inv);
-  }
-}
-
 int attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
                    cudaStream_t stream) {
-  if (!qkv || !key_mask || !out || batch <= 0 || T <= 0 || T > TX_MAXT || dh != 64) return CACO_ERR_ARG;
-  const int smem = 2 * T * TX_LD * 2 + T * 4;
+  if (!qkv || !key_mask || !out || batch <= 0 || T <= 0 || heads <= 0 || dh != 64) return CACO_ERR_ARG;
+  // the flash-style warp-MMA kernel with the causal predicate: one CTA per (64 query rows, head, caption).  The scalar
+  // per-(caption, head) kernel above took 0.10 ms per layer at B = 256, T = 32 (latency-bound shuffle chains).
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TX_MAXT * TX_LD * 2 + TX_MAXT * 4);
+    cudaError_t e = cudaFuncSetAttribute(attention_audio_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES);
     if (e) return (int)e;
     attr = true;
   }
-  dim3 grid(heads, batch);
-  attention_text_kernel<<<grid, 128, smem, stream>>>((const __half*)qkv, key_mask, (__half*)out, T, heads, 1.0f / sqrtf((float)dh));
+  dim3 grid((T + AT_BM - 1) / AT_BM, heads, batch);
+  attention_audio_kernel<64, true><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>(
+      (const __half*)qkv, key_mask, (__half*)out, T, heads, (1.0f / sqrtf((float)dh)) * 1.4426950408889634f);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -324,8 +324,8 @@ class CACO(nn.Module):
         if ids.dim() != 2:
             raise ValueError("text_input_ids: expected [batch, seq]")
         B, T = ids.shape
-        if T > 256 or T > self.text_config.max_position_embeddings:
-            raise ValueError("text sequence length must be <= 256")
+        if T > self.text_config.max_position_embeddings:
+            raise ValueError(f"text sequence length must be <= {self.text_config.max_position_embeddings}")
         mk = _as(text_mask, torch.float32, dev, "text_mask")
         if tuple(mk.shape) != (B, T):
             raise ValueError(f"text_mask: expected shape {(B, T)}")

@@ -82,8 +82,9 @@ int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds,
 int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                          void* stream);
 
-/* 0 = default (persistent tcgen05 kernel for head_dim 96), 1 = warp-level mma.sync kernel (head_dim 64 / 96),
- * 2 = one-tile tcgen05 kernel, 3 = persistent tcgen05 kernel.  1 and 2 are kept as cross-checks / debugging aids. */
+/* 0 = default (persistent ping-pong tcgen05 kernel for head_dim 96, = 4), 1 = warp-level mma.sync kernel (head_dim
+ * 64 / 96), 2 = one-tile tcgen05 kernel, 3 = persistent tcgen05 kernel with P in shared memory, 4 = ping-pong kernel with P
+ * in tensor memory.  1-3 are kept as cross-checks / debugging aids. */
 void caco_set_attention_impl(int impl);
 
 /* ---- K3b: causal text self-attention (roberta.py:86-102, mask from roberta.py:297-310):

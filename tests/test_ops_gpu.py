@@ -123,7 +123,7 @@ def test_attention_audio_sharp_scores():
     assert float((out - ref).norm() / ref.norm()) < 1e-3
 
 
-@pytest.mark.parametrize("T,lens", [(32, [32, 20, 9, 4]), (100, [8, 10, 12, 100]), (1, [1]), (33, [33, 2])])
+@pytest.mark.parametrize("T,lens", [(32, [32, 20, 9, 4]), (100, [8, 10, 12, 100]), (1, [1]), (33, [33, 2]), (200, [200, 130])])
 def test_attention_text_matches_reference_math(T, lens):
     g = torch.Generator().manual_seed(T)
     B, H = len(lens), 12
