@@ -197,8 +197,9 @@ static int pack(caco_model* m, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------- audio tower
-static int audio_chunk(caco_model* m, const float* patches, const float* t_inds, const float* f_inds, const float* mask,
-                       int B, int S, int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
+// patches (fp32) or patches16 (fp16 operand copy already made by the frontend): exactly one is non-null
+static int audio_chunk(caco_model* m, const float* patches, const __half* patches16, const float* t_inds, const float* f_inds,
+                       const float* mask, int B, int S, int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
   const caco_config& c = m->cfg;
   const int D = c.hidden, F = c.ffn, P = c.patch_dim;
   const size_t R = (size_t)B * S;
@@ -222,8 +223,8 @@ static int audio_chunk(caco_model* m, const float* patches, const float* t_inds,
   const int Ri = (int)R;
 
   // input projection + position embeddings (mae.py:133-142)
-  CK(cast_f32_f16(patches, p16, (int64_t)R * P, st));
-  CK(gemm_f16(p16, P, m->in_w, P, m->in_b, nullptr, 0, x, D, Ri, D, P, CACO_EPI_BIAS_F32, 0, 0, st));
+  if (patches16 == nullptr) CK(cast_f32_f16(patches, p16, (int64_t)R * P, st));
+  CK(gemm_f16(patches16 ? patches16 : p16, P, m->in_w, P, m->in_b, nullptr, 0, x, D, Ri, D, P, CACO_EPI_BIAS_F32, 0, 0, st));
   CK(audio_add_pos(x, t_inds, f_inds, m->freq_emb, c.n_freq, Ri, D, st));
   // pre-LN blocks (mae.py:80-99)
   for (int i = 0; i < c.audio_layers; ++i) {
@@ -248,10 +249,11 @@ static int audio_chunk(caco_model* m, const float* patches, const float* t_inds,
   return 0;
 }
 
-static int audio_embedding(caco_model* m, const float* patches, const float* t_inds, const float* f_inds, const float* mask,
-                           int B, int S, int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
+static int audio_embedding(caco_model* m, const float* patches, const __half* patches16, const float* t_inds,
+                           const float* f_inds, const float* mask, int B, int S, int normalize, float* emb_out,
+                           float* hidden_out, cudaStream_t st) {
   if (!m || !m->packed) return CACO_ERR_STATE;
-  if (!patches || !t_inds || !f_inds || !mask || !emb_out || B <= 0 || S <= 0) return CACO_ERR_ARG;
+  if ((!patches && !patches16) || !t_inds || !f_inds || !mask || !emb_out || B <= 0 || S <= 0) return CACO_ERR_ARG;
   const caco_config& c = m->cfg;
   // bound the workspace: at most ~131072 token rows per pass (256 clips of 500 tokens)
   int chunk = (int)(131072 / S);
@@ -259,7 +261,8 @@ static int audio_embedding(caco_model* m, const float* patches, const float* t_i
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
     const size_t r0 = (size_t)b0 * S;
-    CK(audio_chunk(m, patches + r0 * c.patch_dim, t_inds + r0, f_inds + r0, mask + r0, nb, S, normalize,
+    CK(audio_chunk(m, patches ? patches + r0 * c.patch_dim : nullptr, patches16 ? patches16 + r0 * c.patch_dim : nullptr,
+                   t_inds + r0, f_inds + r0, mask + r0, nb, S, normalize,
                    emb_out + (size_t)b0 * c.hidden, hidden_out ? hidden_out + r0 * c.hidden : nullptr, st));
   }
   return 0;
@@ -370,7 +373,7 @@ int caco_model_pack(caco_model* m, void* stream) {
 int caco_model_audio_embedding(caco_model* m, const float* patches, const float* time_inds, const float* freq_inds,
                                const float* mask, int batch, int seq, int normalize, float* emb_out, float* hidden_out,
                                void* stream) {
-  return caco::audio_embedding(m, patches, time_inds, freq_inds, mask, batch, seq, normalize, emb_out, hidden_out,
+  return caco::audio_embedding(m, patches, nullptr, time_inds, freq_inds, mask, batch, seq, normalize, emb_out, hidden_out,
                                (cudaStream_t)stream);
 }
 
@@ -383,14 +386,17 @@ int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_s
                             float* emb_out, void* stream) {
   if (!m || !m->packed) return CACO_ERR_STATE;
   if (!wave || !emb_out || batch <= 0) return CACO_ERR_ARG;
-  // frontend outputs live in a side allocation so the tower's workspace carve-up stays independent
+  // frontend outputs live in a side allocation so the tower's workspace carve-up stays independent; the tower only needs
+  // the fp16 operand copy of the patches, so the fp32 patches are never written on this path
   const size_t R = (size_t)batch * max_patches;
-  float* buf = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&buf, (R * 256 + 3 * R) * sizeof(float), (cudaStream_t)stream);
+  uint8_t* buf = nullptr;
+  const size_t p16_bytes = (R * 256 * sizeof(__half) + 255) & ~(size_t)255;
+  cudaError_t e = cudaMallocAsync((void**)&buf, p16_bytes + 3 * R * sizeof(float), (cudaStream_t)stream);
   if (e) return (int)e;
-  float *patches = buf, *ti = buf + R * 256, *fi = ti + R, *mk = fi + R;
-  int rc = caco::frontend(wave, batch, n_samples, max_patches, patches, nullptr, ti, fi, mk, nullptr, (cudaStream_t)stream);
-  if (!rc) rc = caco::audio_embedding(m, patches, ti, fi, mk, batch, max_patches, normalize, emb_out, nullptr, (cudaStream_t)stream);
+  __half* p16 = (__half*)buf;
+  float *ti = (float*)(buf + p16_bytes), *fi = ti + R, *mk = fi + R;
+  int rc = caco::frontend(wave, batch, n_samples, max_patches, nullptr, p16, ti, fi, mk, nullptr, (cudaStream_t)stream);
+  if (!rc) rc = caco::audio_embedding(m, nullptr, p16, ti, fi, mk, batch, max_patches, normalize, emb_out, nullptr, (cudaStream_t)stream);
   cudaFreeAsync(buf, (cudaStream_t)stream);
   return rc;
 }

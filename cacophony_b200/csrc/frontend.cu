@@ -4,7 +4,7 @@
 //
 // One CTA per (clip, 16-frame group) = one patch row t: it stages the 2912 samples the 16 frames touch,
 // runs 16 real 512-point FFTs in shared memory (256-point complex radix-4 Stockham + real split, fp32,
-// sincospif twiddles), applies the sparse HTK filterbank (505 non-zeros), log(x+1e-5)*0.2+0.9, and
+// host-computed twiddle table), applies the sparse HTK filterbank (505 non-zeros), log(x+1e-5)*0.2+0.9, and
 // writes the 8 patches of that row — 8 KB contiguous in the [B, max_patches, 256] layout — with
 // coalesced 128-byte stores.  HBM-bound by design: 1.158 MB per 10 s clip.
 #include <cuda_runtime.h>
@@ -32,6 +32,8 @@ struct MelTable {
   float w[FE_NMEL][FE_MAXW];
 };
 __device__ MelTable g_mel;
+__device__ float2 g_twiddle[FE_NFFT];   // e^{-2 pi i k / 512}, computed in double on the host
+__device__ float g_window[FE_WIN];      // periodic Hann(400)
 
 // torch.linspace(start, end, steps) in fp32: symmetric evaluation from both ends.
 static void linspace_f32(float start, float end, int steps, std::vector<float>& out) {
@@ -79,6 +81,17 @@ static int frontend_init() {
       for (int j = 0; j < FE_MAXW; ++j) t.w[m][j] = (j < t.count[m]) ? fb[(t.start[m] + j) * FE_NMEL + m] : 0.0f;
     }
     cudaError_t e = cudaMemcpyToSymbol(g_mel, &t, sizeof(t));
+    if (e != cudaSuccess) { rc = (int)e; return; }
+    std::vector<float2> tw(FE_NFFT);
+    for (int k = 0; k < FE_NFFT; ++k) {
+      const double ang = -2.0 * M_PI * (double)k / (double)FE_NFFT;
+      tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    e = cudaMemcpyToSymbol(g_twiddle, tw.data(), sizeof(float2) * FE_NFFT);
+    if (e != cudaSuccess) { rc = (int)e; return; }
+    std::vector<float> win(FE_WIN);
+    for (int i = 0; i < FE_WIN; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)FE_WIN));   // torch.hann_window(400)
+    e = cudaMemcpyToSymbol(g_window, win.data(), sizeof(float) * FE_WIN);
     if (e != cudaSuccess) rc = (int)e;
   });
   return rc;
@@ -122,7 +135,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
         const int p = t * 8 + (i >> 8);
         if (p < max_patches) {
           const size_t o = ((size_t)b * max_patches + p) * 256 + (i & 255);
-          patches[o] = 0.0f;
+          if (patches) patches[o] = 0.0f;
           if (patches_f16) patches_f16[o] = __float2half_rn(0.0f);
         }
       }
@@ -137,12 +150,8 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
     const int s = s0 + i;
     s_x[i] = (s < n_samples) ? __ldg(wv + s) : 0.0f;
   }
-  for (int i = tid; i < FE_NFFT; i += 256) {
-    float sn, cs;
-    sincospif(-(float)i / 256.0f, &sn, &cs);
-    s_tw[i] = make_float2(cs, sn);
-  }
-  for (int i = tid; i < FE_WIN; i += 256) s_win[i] = 0.5f - 0.5f * cospif((float)i / 200.0f);  // periodic Hann(400)
+  for (int i = tid; i < FE_NFFT; i += 256) s_tw[i] = g_twiddle[i];
+  for (int i = tid; i < FE_WIN; i += 256) s_win[i] = g_window[i];
   __syncthreads();
 
   const int slot = tid >> 6;  // frame slot 0..3
@@ -222,7 +231,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
       if (p < max_patches) {
         const float v = s_out[e >> 4][16 * f + (e & 15)];
         const size_t o = ((size_t)b * max_patches + p) * 256 + e;
-        patches[o] = v;
+        if (patches) patches[o] = v;
         if (patches_f16) patches_f16[o] = __float2half_rn(v);
       }
     }
@@ -231,7 +240,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
       const int p = t * 8 + (i >> 8);
       if (p < max_patches) {
         const size_t o = ((size_t)b * max_patches + p) * 256 + (i & 255);
-        patches[o] = 0.0f;
+        if (patches) patches[o] = 0.0f;
         if (patches_f16) patches_f16[o] = __float2half_rn(0.0f);
       }
     }
@@ -240,7 +249,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
 
 int frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
              float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream) {
-  if (!wave || !patches || !time_inds || !freq_inds || !mask || batch <= 0 || n_samples <= 0 || max_patches <= 0)
+  if (!wave || (!patches && !patches_f16) || !time_inds || !freq_inds || !mask || batch <= 0 || n_samples <= 0 || max_patches <= 0)
     return CACO_ERR_ARG;
   int rc = frontend_init();
   if (rc) return rc;

@@ -198,7 +198,8 @@ int text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* 
 // One CTA (256 threads) per sample.  Phase 1: per token row (one warp each) optional LayerNorm, scores against the
 // folded queries u[h].  Phase 2: masked softmax per head.  Phase 3: weighted sum of the (normalised) rows.
 constexpr int POOL_MAX_HEADS = 4;
-__global__ void __launch_bounds__(256)
+constexpr int POOL_THREADS = 512, POOL_WARPS = POOL_THREADS / 32;   // 16 rows in flight per CTA in phase 1
+__global__ void __launch_bounds__(POOL_THREADS)
 attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, const float* __restrict__ u,
                  const float* __restrict__ cvec, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
                  float* __restrict__ hid_out, float* __restrict__ pooled, int S, int heads, int dim) {
@@ -206,7 +207,7 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
   float* s_score = sm;                  // [heads][S]
   float* s_mean = sm + heads * S;       // [S]
   float* s_rstd = s_mean + S;           // [S]
-  __shared__ float s_red[POOL_MAX_HEADS][8];
+  __shared__ float s_red[POOL_MAX_HEADS][POOL_WARPS];
   __shared__ float s_stat[POOL_MAX_HEADS][2];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hb = hid + (size_t)b * S * dim;
@@ -214,7 +215,7 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
   const int nv = dim / 128;
   const bool do_ln = ln_g != nullptr;
 
-  for (int j = warp; j < S; j += 8) {
+  for (int j = warp; j < S; j += POOL_WARPS) {
     float4 v[ROW_MAX_V4];
 #pragma unroll
     for (int c = 0; c < ROW_MAX_V4; ++c)
@@ -253,21 +254,21 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
   // softmax per head (max, exp, sum) over S
   for (int h = 0; h < heads; ++h) {
     float mx = -INFINITY;
-    for (int j = tid; j < S; j += 256) mx = fmaxf(mx, s_score[h * S + j]);
+    for (int j = tid; j < S; j += POOL_THREADS) mx = fmaxf(mx, s_score[h * S + j]);
     mx = warp_max(mx);
     if (lane == 0) s_red[h][warp] = mx;
   }
   __syncthreads();
   if (tid < heads) {
     float mx = -INFINITY;
-    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_red[tid][w]);
+    for (int w = 0; w < POOL_WARPS; ++w) mx = fmaxf(mx, s_red[tid][w]);
     s_stat[tid][0] = mx;
   }
   __syncthreads();
   for (int h = 0; h < heads; ++h) {
     const float mx = s_stat[h][0];
     float sum = 0.f;
-    for (int j = tid; j < S; j += 256) {
+    for (int j = tid; j < S; j += POOL_THREADS) {
       const float e = expf(s_score[h * S + j] - mx);
       s_score[h * S + j] = e;
       sum += e;
@@ -278,16 +279,17 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
   __syncthreads();
   if (tid < heads) {
     float sum = 0.f;
-    for (int w = 0; w < 8; ++w) sum += s_red[tid][w];
+    for (int w = 0; w < POOL_WARPS; ++w) sum += s_red[tid][w];
     s_stat[tid][1] = 1.0f / sum;
   }
   __syncthreads();
   // weighted sum: thread owns columns tid, tid+256, ...
-  for (int col = tid; col < dim; col += 256) {
+  for (int col = tid; col < dim; col += POOL_THREADS) {
     float acc[POOL_MAX_HEADS];
 #pragma unroll
     for (int h = 0; h < POOL_MAX_HEADS; ++h) acc[h] = 0.f;
     const float g = do_ln ? ln_g[col] : 1.f, bt = do_ln ? ln_b[col] : 0.f;
+#pragma unroll 8
     for (int j = 0; j < S; ++j) {
       float xv = hb[(size_t)j * dim + col];
       if (do_ln) xv = (xv - s_mean[j]) * s_rstd[j] * g + bt;
@@ -312,7 +314,7 @@ int attn_pool(const float* hid, const float* mask, const float* u, const float* 
     if (e) return (int)e;
     cur_max = smem;
   }
-  attn_pool_kernel<<<batch, 256, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, heads, dim);
+  attn_pool_kernel<<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, heads, dim);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -343,40 +345,47 @@ int fold_query(const float* query, const float* wk, const float* bk, float qscal
 }
 
 // ------------------------------------------------------------------------------------------------ small fp32 GEMM
-// out[M,N] = alpha * A[M,K] · W[N,K]^T + bias.  64x64 tile, 256 threads, 4x4 micro-tile, K step 16.
-// alpha = alpha_scalar * (log_alpha ? exp(*log_alpha) : 1).
-__global__ void __launch_bounds__(256)
+// out[M,N] = alpha * A[M,K] · W[N,K]^T + bias for the [batch, 768]-sized tails.  32x32 tile, 64 threads, 4x4 micro-tile,
+// K step 32, next K slab prefetched into registers while the current one is multiplied: at M = 256 the grid is
+// (N/32) x 8 CTAs, so even the 256x384 value projection fills the 148 SMs.  alpha = alpha_scalar * (log_alpha ?
+// exp(*log_alpha) : 1).  K % 4 == 0 (float4 loads), edges handled by zero fill.
+__global__ void __launch_bounds__(64)
 sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                 float alpha, const float* __restrict__ log_alpha, float* __restrict__ out, int ldo, int M, int N, int K) {
-  __shared__ float sA[16][64 + 4];
-  __shared__ float sW[16][64 + 4];
+  __shared__ float sA[32][32 + 4];   // [k][m]
+  __shared__ float sW[32][32 + 4];   // [k][n]
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = tid & 7, ty = tid >> 3;        // 8 x 8 threads, 4 x 4 outputs each
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int lr = tid >> 2;          // 0..63: tile row loaded by this thread
-  const int lk = (tid & 3) * 4;     // 0,4,8,12: k offset
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
-    if (m0 + lr < M) {
-      const float* p = A + (size_t)(m0 + lr) * lda + k0 + lk;
-      if (k0 + lk + 3 < K) a = *reinterpret_cast<const float4*>(p);
-      else { if (k0 + lk < K) a.x = p[0]; if (k0 + lk + 1 < K) a.y = p[1]; if (k0 + lk + 2 < K) a.z = p[2]; }
-    }
-    if (n0 + lr < N) {
-      const float* p = W + (size_t)(n0 + lr) * ldw + k0 + lk;
-      if (k0 + lk + 3 < K) w = *reinterpret_cast<const float4*>(p);
-      else { if (k0 + lk < K) w.x = p[0]; if (k0 + lk + 1 < K) w.y = p[1]; if (k0 + lk + 2 < K) w.z = p[2]; }
-    }
-    sA[lk][lr] = a.x; sA[lk + 1][lr] = a.y; sA[lk + 2][lr] = a.z; sA[lk + 3][lr] = a.w;
-    sW[lk][lr] = w.x; sW[lk + 1][lr] = w.y; sW[lk + 2][lr] = w.z; sW[lk + 3][lr] = w.w;
-    __syncthreads();
+  // loader mapping: 32 rows x 8 float4 per slab = 256 float4 per operand, 4 per thread
+  float4 ra[4], rw[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + q * 64, r = idx >> 3, kq = (idx & 7) * 4;
+      ra[q] = (m0 + r < M && k0 + kq < K) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + kq)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[q] = (n0 + r < N && k0 + kq < K) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * ldw + k0 + kq)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + q * 64, r = idx >> 3, kq = (idx & 7) * 4;
+      sA[kq][r] = ra[q].x; sA[kq + 1][r] = ra[q].y; sA[kq + 2][r] = ra[q].z; sA[kq + 3][r] = ra[q].w;
+      sW[kq][r] = rw[q].x; sW[kq + 1][r] = rw[q].y; sW[kq + 2][r] = rw[q].z; sW[kq + 3][r] = rw[q].w;
+    }
+    __syncthreads();
+    if (k0 + 32 < K) fetch(k0 + 32);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
       const float4 av = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
       const float4 wv = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
       const float ar[4] = {av.x, av.y, av.z, av.w};
@@ -403,10 +412,10 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 static int sgemm_impl(const float* A, int lda, const float* W, int ldw, const float* bias, float alpha,
                       const float* log_alpha, float* out, int ldo, int M, int N, int K, cudaStream_t stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
-  if ((lda & 3) || (ldw & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+  if ((lda & 3) || (ldw & 3) || (K & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return CACO_ERR_ALIGN;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_nt_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, alpha, log_alpha, out, ldo, M, N, K);
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  sgemm_nt_kernel<<<grid, 64, 0, stream>>>(A, lda, W, ldw, bias, alpha, log_alpha, out, ldo, M, N, K);
   count_launch();
   return (int)cudaGetLastError();
 }
