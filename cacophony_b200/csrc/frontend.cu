@@ -16,6 +16,7 @@
 
 #include "caco_b200.h"
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace caco {
 
@@ -190,7 +191,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
       dst[idx + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
       dst[idx + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
       if (stage > 0) cur ^= 1;
-      __syncthreads();
+      named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
     }
     // ---- real split: X[k] = E + W^k O, |X[k]|, k = 0..256
     const float2* Z = s_buf[cur][slot];
@@ -205,7 +206,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
       const float xi = ei + (w.x * oi + w.y * orr);
       s_mag[slot][k] = sqrtf(xr * xr + xi * xi);
     }
-    __syncthreads();
+    named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
     // ---- sparse mel + log (eval_caco_torch.py:103-104)
     for (int m = j; m < FE_NMEL; m += 64) {
       const int st = g_mel.start[m], cnt = g_mel.count[m];  // 9 KB table, L1/L2 resident
@@ -213,9 +214,10 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
       for (int q = 0; q < cnt; ++q) acc = fmaf(s_mag[slot][st + q], g_mel.w[m][q], acc);
       s_out[dt][m] = logf(acc + 1e-5f) * 0.2f + 0.9f;
     }
-    __syncthreads();
+    named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
   }
 
+  __syncthreads();   // all four 64-thread groups have filled their rows of s_out
   // ---- optional raw log-mel [B, n_frames, 128]
   if (log_mel != nullptr) {
     for (int i = tid; i < FE_FRAMES * FE_NMEL; i += 256) {
