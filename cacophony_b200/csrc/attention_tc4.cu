@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "caco_b200.h"
 #include "common.cuh"
@@ -53,6 +54,18 @@ __device__ long long* g_attn4_trace = nullptr;
   do {                                                                                        \
     if (trace != nullptr && (blk) < 64) trace[((role) * 64 + (blk)) * 8 + (ev)] = clock64(); \
   } while (0)
+
+// mbarrier wait with a watchdog: a protocol bug traps with a message instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int id, int g) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      printf("attention_tc4: barrier timeout id=%d g=%d parity=%u cta=%d warp=%d lane=%d\n", id, g, parity, (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
+      __trap();
+    }
+  }
+}
 
 struct Attn4Args {
   const float* mask;
@@ -120,7 +133,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       decode(it, b, h, q0);
       for (int j = 0; j < nb; ++j) {
         const int g = it * nb + j, st = g % NST;
-        if (g >= NST) mbar_wait(bar + B_KEMPTY + 8 * st, ((g / NST) + 1) & 1);
+        if (g >= NST) mbar_wait_wd(bar + B_KEMPTY + 8 * st, ((g / NST) + 1) & 1, 1, g);
         if (lane == 0) {
           const uint32_t kf = bar + B_KFULL + 8 * st;
           mbar_expect_tx(kf, K_TILE);
@@ -137,7 +150,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       decode(it, b, h, q0);
       for (int j = 0; j < nb; ++j) {
         const int g = it * nb + j, st = g % NST;
-        if (g >= NST) mbar_wait(bar + B_VEMPTY + 8 * st, ((g / NST) + 1) & 1);
+        if (g >= NST) mbar_wait_wd(bar + B_VEMPTY + 8 * st, ((g / NST) + 1) & 1, 2, g);
         if (lane == 0) {
           const uint32_t vf = bar + B_VFULL + 8 * st;
           mbar_expect_tx(vf, V_TILE);
@@ -153,7 +166,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       int b, h, q0;
       decode(it, b, h, q0);
       const int ib = it & 1;
-      if (it >= 2) mbar_wait(bar + B_ITEMDONE + 8 * ib, ((it >> 1) + 1) & 1);
+      if (it >= 2) mbar_wait_wd(bar + B_ITEMDONE + 8 * ib, ((it >> 1) + 1) & 1, 3, it);
       if (lane == 0) {
         const uint32_t qf = bar + B_QFULL + 8 * ib;
         mbar_expect_tx(qf, 2 * Q_TILE);
@@ -196,8 +209,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
     };
     auto wait_qk_inputs = [&](int g) {
       const int it = g / nb;
-      if (g % nb == 0) mbar_wait(bar + B_QFULL + 8 * (it & 1), (it >> 1) & 1);
-      mbar_wait(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1);
+      if (g % nb == 0) mbar_wait_wd(bar + B_QFULL + 8 * (it & 1), (it >> 1) & 1, 4, it);
+      mbar_wait_wd(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1, 5, g);
       tc_fence_after();
     };
     for (int g = 0; g < 2 && g < total; ++g) {    // prologue: both S buffers of both tiles
@@ -209,12 +222,12 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       TC4_STAMP(0, g, 0);
       const int st = g % NST, sbuf = g & 1;
       const uint32_t acc0 = (g % nb) ? 1u : 0u;
-      mbar_wait(bar + B_VFULL + 8 * st, (g / NST) & 1);
+      mbar_wait_wd(bar + B_VFULL + 8 * st, (g / NST) & 1, 6, g);
       if (g + 2 < total) wait_qk_inputs(g + 2);
       TC4_STAMP(0, g, 1);
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
-        mbar_wait(bar + B_PFULL + 8 * x, g & 1);
+        mbar_wait_wd(bar + B_PFULL + 8 * x, g & 1, 7, g);
         TC4_STAMP(0, g, 2 + 2 * x);
         tc_fence_after();
         if (lane == 0) {
@@ -247,7 +260,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       const int it = g / nb, j = g - it * nb, ib = it & 1, sbuf = g & 1;
       if (j == 0) {
         decode(it, b, h, q0);
-        mbar_wait(bar + B_BIASFULL + 8 * ib, (it >> 1) & 1);
+        mbar_wait_wd(bar + B_BIASFULL + 8 * ib, (it >> 1) & 1, 8, it);
         m_ref = -INFINITY;
         l_run = 0.f;
       }
@@ -255,7 +268,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       const float* bias = s_bias + ib * a.max_keys + j * BN;
       const uint32_t t_s = t_lane + TM_S + (x * 2 + sbuf) * BN;
       TC4_STAMP(1, g, 0);
-      mbar_wait(b_sfull + 8 * sbuf, (g >> 1) & 1);
+      mbar_wait_wd(b_sfull + 8 * sbuf, (g >> 1) & 1, 9, g);
       TC4_STAMP(1, g, 1);
       tc_fence_after();
       uint32_t v[2][32];
@@ -286,7 +299,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       if (__any_sync(0xffffffffu, need)) {
         const float factor = need ? exp2f(m_ref - mx) : 1.0f;
         if (j > 0) {
-          mbar_wait(b_pvdone, (g - 1) & 1);                   // O_x must hold every P V of this item issued so far
+          mbar_wait_wd(b_pvdone, (g - 1) & 1, 10, g);                   // O_x must hold every P V of this item issued so far
           tc_fence_after();
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {
@@ -329,7 +342,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q64, const __grid_c
       TC4_STAMP(1, g, 3);
       if (j == nb - 1) {
         // ---- item epilogue: O / l -> fp16 (the next item's first P V needs this warp's next P, so O_x is safe to read)
-        mbar_wait(b_pvdone, g & 1);
+        mbar_wait_wd(b_pvdone, g & 1, 10, g);
         TC4_STAMP(1, g, 4);
         tc_fence_after();
         const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
