@@ -248,16 +248,13 @@ int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch
                         cudaStream_t stream);
 int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                         cudaStream_t stream);
-int attention_audio_tc4(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
-                        cudaStream_t stream);
 static int g_attn_impl = 0;   // 0 = auto, 1 = warp-level mma.sync kernel, 2 = tcgen05 one-tile kernel, 3 = tcgen05 persistent kernel
 
 int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                     cudaStream_t stream) {
   if (!qkv || !mask || !out || batch <= 0 || seq <= 0 || heads <= 0) return CACO_ERR_ARG;
-  if (dh == 96 && (g_attn_impl == 0 || g_attn_impl == 5) && seq <= 2304)
-    return attention_audio_tc4(qkv, mask, out, batch, seq, heads, dh, stream);
-  if (dh == 96 && g_attn_impl == 4 && seq <= 2304) return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
+  if (dh == 96 && (g_attn_impl == 0 || g_attn_impl == 4) && seq <= 2304)
+    return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
   if (dh == 96 && g_attn_impl != 1) {
     if (g_attn_impl != 2 && seq <= 1856) return attention_audio_tc2(qkv, mask, out, batch, seq, heads, dh, stream);
     if (seq <= 1728) return attention_audio_tc(qkv, mask, out, batch, seq, heads, dh, stream);

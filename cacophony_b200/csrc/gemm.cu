@@ -57,8 +57,18 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-// x * sigmoid(x) with MUFU ex2 + rcp (2-3 ulp; the result is rounded to fp16 right after)
-__device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op (tanh.approx, rel. error 2^-11 — the rounding the fp16 store
+// applies anyway) instead of ex2 + rcp; the fc1 epilogue was MUFU-latency-bound with two (profiles/r01_notes.md)
+__device__ __forceinline__ float act_silu(float x) {
+#ifdef CACO_SILU_EX2
+  return __fdividef(x, 1.0f + __expf(-x));
+#else
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+#endif
+}
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>

@@ -13,21 +13,21 @@ qkv = torch.randn(B, S, 3 * H * dh, device="cuda").half()
 mask = torch.ones(B, S, device="cuda")
 mask[:, 496:] = 0
 lib = L.load()
-lib.caco_set_attention_impl(5)
-lib.caco_attn4_trace.argtypes = [C.c_void_p]
+lib.caco_set_attention_impl(4)
+lib.caco_attn3_trace.argtypes = [C.c_void_p]
 for _ in range(2):
     ops.attention_audio(qkv, mask, H)
 buf = torch.zeros(2 * 64 * 8, dtype=torch.int64, device="cuda")
-lib.caco_attn4_trace(buf.data_ptr())
+lib.caco_attn3_trace(buf.data_ptr())
 ops.attention_audio(qkv, mask, H)
 torch.cuda.synchronize()
-lib.caco_attn4_trace(None)
+lib.caco_attn3_trace(None)
 t = buf.cpu().view(2, 64, 8)
 t0 = int(t[t > 0].min())
 names = [["iter", "inputs", "pA_seen", "pvA+qkA", "pB_seen", "pvB+qkB", "-", "-"],
          ["wait_s", "s_ready", "max_done", "p_written", "pv_done", "stored", "-", "-"]]
 for role, rn in ((0, "MMA"), (1, "SMX")):
     print(rn, " ".join(f"{n:>10s}" for n in names[role]))
-    for g in range(26):
+    for g in range(14):
         row = t[role, g]
         print(f"g={g:2d}", " ".join(f"{(int(v) - t0) if v > 0 else -1:10d}" for v in row))

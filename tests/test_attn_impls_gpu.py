@@ -12,7 +12,7 @@ from cacophony_b200 import _lib as L
 from cacophony_b200 import ops
 from tests.test_ops_gpu import _attn_ref
 
-IMPLS = {"mma_sync": 1, "tc_one_tile": 2, "tc_persistent": 3, "tc_pingpong": 4, "tc_dbuf": 5}
+IMPLS = {"mma_sync": 1, "tc_one_tile": 2, "tc_persistent": 3, "tc_pingpong": 4}
 
 
 @pytest.fixture(autouse=True)
