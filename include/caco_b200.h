@@ -58,6 +58,9 @@ int caco_frontend(const float* wave, int batch, int n_samples, int max_patches, 
 int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr,
                   void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream);
 void caco_set_gemm_variant(int variant);
+/* CACO_EPI_BIAS_RESID_F32 with resid == out (in-place residual update): 1 (default) = the add is done by the L2 with
+ * red.global.add.v4.f32, 0 = load/add/store in the SM.  Same fp32 result; a measurement switch. */
+void caco_set_gemm_resid_red(int enable);
 /* live profiling for bench.py: CUDA events around every GEMM launch on its stream.  caco_gemm_profile(1) resets and
  * starts recording; caco_gemm_profile_read synchronises the device and returns the launch count, summed device
  * time (ms) and summed algorithmic FLOPs (2*M*N*K). */
