@@ -35,6 +35,7 @@ SIGNATURES = {
     "caco_version": (_I, []),
     "caco_built_arch": (_I, []),
     "caco_frontend": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "caco_frontend_ragged": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "caco_gemm_f16": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "caco_set_gemm_variant": (None, [_I]),
     "caco_set_gemm_resid_red": (None, [_I]),
@@ -58,7 +59,11 @@ SIGNATURES = {
     "caco_model_audio_embedding": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_text_embedding": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_encode_audio": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "caco_model_encode_audio_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "caco_model_logit_scale": (_P, [_P]),
+    "caco_topk_rows": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "caco_retrieval_hits": (_I, [_P, _I, _I, _P, _P, _P, _I, C.c_longlong, _I, _P, _P]),
+    "caco_avg_pool_tokens": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "caco_launch_count": (_L, []),
     "caco_last_error": (C.c_char_p, []),
     "caco_mel_filterbank": (_I, [_P]),

@@ -15,8 +15,8 @@ int num_sms();
 // op-level entry points implemented across the .cu files (C++ side of the C ABI)
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
              int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream);
-int frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
-             float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream);
+int frontend(const float* wave, const int* lengths, int batch, int n_samples, int max_patches, float* patches,
+             void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream);
 int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
               int dim, cudaStream_t stream);

@@ -382,23 +382,38 @@ int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* ma
   return caco::text_embedding(m, ids, mask, position_ids, batch, T, normalize, emb_out, hidden_out, (cudaStream_t)stream);
 }
 
-int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
-                            float* emb_out, void* stream) {
+// waveform-in path: frontend (uniform or ragged) + audio tower.  The frontend outputs live in a side allocation so the
+// tower's workspace carve-up stays independent; the tower only needs the fp16 operand copy of the patches, so the fp32
+// patches are never written on this path.
+static int encode_audio_impl(caco_model* m, const float* wave, const int* lengths, int batch, int stride, int max_patches,
+                             int normalize, float* emb_out, float* hidden_out, float* mask_out, cudaStream_t st) {
   if (!m || !m->packed) return CACO_ERR_STATE;
-  if (!wave || !emb_out || batch <= 0) return CACO_ERR_ARG;
-  // frontend outputs live in a side allocation so the tower's workspace carve-up stays independent; the tower only needs
-  // the fp16 operand copy of the patches, so the fp32 patches are never written on this path
+  if (!wave || !emb_out || batch <= 0 || stride <= 0 || max_patches <= 0) return CACO_ERR_ARG;
   const size_t R = (size_t)batch * max_patches;
   uint8_t* buf = nullptr;
   const size_t p16_bytes = (R * 256 * sizeof(__half) + 255) & ~(size_t)255;
-  cudaError_t e = cudaMallocAsync((void**)&buf, p16_bytes + 3 * R * sizeof(float), (cudaStream_t)stream);
+  cudaError_t e = cudaMallocAsync((void**)&buf, p16_bytes + 3 * R * sizeof(float), st);
   if (e) return (int)e;
   __half* p16 = (__half*)buf;
   float *ti = (float*)(buf + p16_bytes), *fi = ti + R, *mk = fi + R;
-  int rc = caco::frontend(wave, batch, n_samples, max_patches, nullptr, p16, ti, fi, mk, nullptr, (cudaStream_t)stream);
-  if (!rc) rc = caco::audio_embedding(m, nullptr, p16, ti, fi, mk, batch, max_patches, normalize, emb_out, nullptr, (cudaStream_t)stream);
-  cudaFreeAsync(buf, (cudaStream_t)stream);
+  int rc = caco::frontend(wave, lengths, batch, stride, max_patches, nullptr, p16, ti, fi, mk, nullptr, st);
+  if (!rc) rc = caco::audio_embedding(m, nullptr, p16, ti, fi, mk, batch, max_patches, normalize, emb_out, hidden_out, st);
+  if (!rc && mask_out) rc = (int)cudaMemcpyAsync(mask_out, mk, R * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  cudaFreeAsync(buf, st);
   return rc;
+}
+
+int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
+                            float* emb_out, void* stream) {
+  return encode_audio_impl(m, wave, nullptr, batch, n_samples, max_patches, normalize, emb_out, nullptr, nullptr,
+                           (cudaStream_t)stream);
+}
+
+int caco_model_encode_audio_ex(caco_model* m, const float* wave, const int* lengths, int batch, int stride,
+                               int max_patches, int normalize, float* emb_out, float* hidden_out, float* mask_out,
+                               void* stream) {
+  return encode_audio_impl(m, wave, lengths, batch, stride, max_patches, normalize, emb_out, hidden_out, mask_out,
+                           (cudaStream_t)stream);
 }
 
 const float* caco_model_logit_scale(caco_model* m) { return m ? m->logit_scale : nullptr; }

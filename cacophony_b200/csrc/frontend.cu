@@ -101,7 +101,7 @@ static int frontend_init() {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 __global__ void __launch_bounds__(256)
-frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int nt_valid, int max_patches,
+frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths, int stride, int n_samples_u, int max_patches,
                 float* __restrict__ patches, __half* __restrict__ patches_f16, float* __restrict__ time_inds,
                 float* __restrict__ freq_inds, float* __restrict__ mask, float* __restrict__ log_mel) {
   __shared__ float s_x[FE_SAMPLES];
@@ -112,6 +112,14 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
   __shared__ float s_out[FE_FRAMES][FE_MEL_LD];
 
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  // ragged batches: clip b holds lengths[b] samples in a row of `stride` floats (uniform batches: lengths == nullptr)
+  int n_samples = n_samples_u;
+  if (lengths != nullptr) {
+    n_samples = __ldg(lengths + b);
+    n_samples = n_samples < 0 ? 0 : (n_samples > stride ? stride : n_samples);
+  }
+  const int n_frames = (n_samples + FE_HOP - 1) / FE_HOP;  // eval_caco_torch.py:67
+  const int nt_valid = n_frames / 16;                      // eval_caco_torch.py:116-117
   const int frame0 = t * FE_FRAMES;
   const int T_out = (max_patches + 7) / 8;
   const int n_valid_tokens = nt_valid * 8;
@@ -145,7 +153,7 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
   }
 
   // ---- stage samples (zero tail pad, eval_caco_torch.py:72-78), twiddles, window, mel table
-  const float* wv = wave + (size_t)b * n_samples;
+  const float* wv = wave + (size_t)b * stride;
   const int s0 = frame0 * FE_HOP;
   for (int i = tid; i < FE_SAMPLES; i += 256) {
     const int s = s0 + i;
@@ -249,19 +257,19 @@ frontend_kernel(const float* __restrict__ wave, int n_samples, int n_frames, int
   }
 }
 
-int frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
-             float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream) {
+int frontend(const float* wave, const int* lengths, int batch, int n_samples, int max_patches, float* patches,
+             void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream) {
   if (!wave || (!patches && !patches_f16) || !time_inds || !freq_inds || !mask || batch <= 0 || n_samples <= 0 || max_patches <= 0)
     return CACO_ERR_ARG;
+  if (lengths != nullptr && log_mel != nullptr) return CACO_ERR_ARG;   // the raw log-mel output is per-length: uniform batches only
   int rc = frontend_init();
   if (rc) return rc;
-  const int n_frames = (n_samples + FE_HOP - 1) / FE_HOP;  // eval_caco_torch.py:67
-  const int nt_valid = n_frames / 16;                      // eval_caco_torch.py:116-117
+  const int n_frames = (n_samples + FE_HOP - 1) / FE_HOP;
   const int T_out = (max_patches + 7) / 8;
   int gx = T_out;
   if (log_mel != nullptr) gx = max(gx, (n_frames + FE_FRAMES - 1) / FE_FRAMES);
   dim3 grid(gx, batch);
-  frontend_kernel<<<grid, 256, 0, stream>>>(wave, n_samples, n_frames, nt_valid, max_patches, patches,
+  frontend_kernel<<<grid, 256, 0, stream>>>(wave, lengths, n_samples, n_samples, max_patches, patches,
                                             reinterpret_cast<__half*>(patches_f16), time_inds, freq_inds, mask, log_mel);
   count_launch();
   return (int)cudaGetLastError();
@@ -272,7 +280,18 @@ int frontend(const float* wave, int batch, int n_samples, int max_patches, float
 extern "C" int caco_frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches,
                              void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel,
                              void* stream) {
-  return caco::frontend(wave, batch, n_samples, max_patches, patches, patches_f16, time_inds, freq_inds, mask, log_mel,
+  return caco::frontend(wave, nullptr, batch, n_samples, max_patches, patches, patches_f16, time_inds, freq_inds, mask, log_mel,
+                        (cudaStream_t)stream);
+}
+
+// ragged batch: clip b = wave[b*stride : b*stride + lengths[b]] (lengths: DEVICE int32 [batch]); every clip gets the
+// reference's per-clip treatment (its own frame count, valid-patch count, zero padding, mask) — eval_caco_torch.py:181-206
+// applied clip by clip, in one launch
+extern "C" int caco_frontend_ragged(const float* wave, const int* lengths, int batch, int stride, int max_patches,
+                                    float* patches, void* patches_f16, float* time_inds, float* freq_inds, float* mask,
+                                    void* stream) {
+  if (!lengths) return CACO_ERR_ARG;
+  return caco::frontend(wave, lengths, batch, stride, max_patches, patches, patches_f16, time_inds, freq_inds, mask, nullptr,
                         (cudaStream_t)stream);
 }
 

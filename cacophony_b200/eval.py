@@ -1,0 +1,294 @@
+"""Row (f-2 / f-3): the callers on either side of the hot path, with the reference's names
+(src/eval/eval_caco_torch.py:154-408, src/eval/eval_utils.py:18-66), batched and with the O(N·M) parts on the device.
+
+Reference flow (one clip and one caption per model call, batch dimension 1, argsort of whole logit rows on the
+device then numpy on the host)            ->  here
+  compute_all_class_embeddings :264-286   ->  one tokenizer call for all prompts, text tower in batches
+  zs_classification            :289-340   ->  clips batched through the ragged frontend + audio tower, ONE logits matrix
+                                              exp(logit_scale)·A·Tᵀ (caco_sim_logits), top-k per row (caco_topk_rows)
+  audio_retrieval              :343-408   ->  both towers batched, T·Aᵀ and A·Tᵀ (caco_sgemm_nt), top-10 per row,
+                                              per-query hit masks (caco_retrieval_hits); only [queries] int32 reach the host
+  compute_retrieval_metric  eval_utils:18  ->  same R@1/5/10, mAP@10 and jackknife 95 % intervals, float64 on the host
+
+Not available offline and therefore injected by the caller: the ``roberta-base`` tokenizer (any callable with the
+``RobertaTokenizerFast.__call__`` keyword interface) and the dataset processors (anything with
+``get_filepaths_and_descriptions`` and ``config.sampling_rate``).  The ``*_arrays`` entry points take in-memory
+waveforms instead of file paths.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import loader, ops
+from .frontend import DatasetConfig, prepare_audio_batch
+from .model import CACO, create_caco_model
+
+
+# ----------------------------------------------------------------------------------------------------------- loading
+def load_caco_torch(ckpt_path: Optional[str], device: Union[str, torch.device], tokenizer: Any = None,
+                    state_dict: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, Any]:
+    """eval_caco_torch.py:154-178.  Accepts the three checkpoint layouts the reference accepts ('model_state_dict',
+    'state_dict', or a bare state_dict); ``decoder_module.*`` tensors are ignored.  The tokenizer cannot be downloaded here:
+    pass one in (``RobertaTokenizerFast.from_pretrained('roberta-base')`` where the files exist)."""
+    model = create_caco_model()
+    if state_dict is None:
+        if ckpt_path is None:
+            raise ValueError("load_caco_torch: ckpt_path or state_dict required")
+        checkpoint = torch.load(ckpt_path, map_location="cpu")
+    else:
+        checkpoint = state_dict
+    if "model_state_dict" in checkpoint:
+        model.load_state_dict(checkpoint["model_state_dict"])
+    elif "state_dict" in checkpoint:
+        model.load_state_dict(checkpoint["state_dict"])
+    else:
+        model.load_state_dict(checkpoint)
+    model = model.to(device)
+    model.eval()
+    if tokenizer is None:
+        try:
+            from transformers import RobertaTokenizerFast
+            tokenizer = RobertaTokenizerFast.from_pretrained("roberta-base", local_files_only=True)
+        except Exception:
+            tokenizer = None          # offline: callers pass token ids / their own tokenizer
+    return {"model": model, "tokenizer": tokenizer, "device": torch.device(device)}
+
+
+def prepare_text_batch(text: Union[str, Sequence[str]], tokenizer: Any, max_text_len: int,
+                       device: Union[str, torch.device]) -> Dict[str, torch.Tensor]:
+    """eval_caco_torch.py:209-227 for one caption or a list of captions."""
+    if tokenizer is None:
+        raise ValueError("prepare_text_batch: a tokenizer is required (roberta-base files are not available offline)")
+    texts = [text] if isinstance(text, str) else list(text)
+    tokenized = tokenizer(texts, padding="max_length", truncation=True, max_length=max_text_len, return_tensors="pt")
+    return {"text_input_ids": tokenized["input_ids"].to(device), "text_mask": tokenized["attention_mask"].to(device)}
+
+
+@torch.no_grad()
+def compute_audio_embedding(model: CACO, audio_batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """eval_caco_torch.py:230-245."""
+    return model.get_audio_embedding(audio_patches=audio_batch["audio_patches"], audio_time_inds=audio_batch["audio_time_inds"],
+                                     audio_freq_inds=audio_batch["audio_freq_inds"], audio_mask=audio_batch["audio_mask"],
+                                     deterministic=True, return_hidden_state=False, normalize=True)
+
+
+@torch.no_grad()
+def compute_text_embedding(model: CACO, text_batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """eval_caco_torch.py:248-261."""
+    return model.get_text_embedding(text_input_ids=text_batch["text_input_ids"], text_mask=text_batch["text_mask"],
+                                    deterministic=True, return_hidden_state=False, normalize=True)
+
+
+@torch.no_grad()
+def embed_text_ids(model: CACO, ids: torch.Tensor, mask: torch.Tensor, batch_size: int = 512) -> torch.Tensor:
+    """L2-normalised text embeddings of already-tokenised captions, in batches."""
+    outs = []
+    for i in range(0, ids.shape[0], batch_size):
+        outs.append(model.encode_text(ids[i:i + batch_size], mask[i:i + batch_size]))
+    return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+
+@torch.no_grad()
+def embed_waveforms(model: CACO, waves: Sequence[Any], datasetconfig: Optional[DatasetConfig] = None, batch_size: int = 256,
+                    trim_padding: bool = True) -> torch.Tensor:
+    """L2-normalised audio embeddings of a list of (ragged) 16 kHz clips: pinned ragged packing -> async H2D -> ragged frontend
+    + audio tower, `batch_size` clips per library call."""
+    cfg = datasetconfig or DatasetConfig()
+    dev = model._device()
+    outs = []
+    for i in range(0, len(waves), batch_size):
+        buf, lens = loader.pad_ragged(waves[i:i + batch_size])
+        w = buf.to(dev, non_blocking=True)
+        outs.append(model.encode_audio(w, max_patches=cfg.patches_seq_len, lengths=lens, trim_padding=trim_padding))
+    return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+
+@torch.no_grad()
+def compute_all_class_embeddings(model: CACO, tokenizer: Any, class_list: List[str], max_text_len: int,
+                                 device: Union[str, torch.device], prefix: str = "", batch_size: int = 512) -> torch.Tensor:
+    """eval_caco_torch.py:264-286: [n_classes, 768], one tokenizer call, text tower in batches."""
+    tb = prepare_text_batch([prefix + c for c in class_list], tokenizer, max_text_len, device)
+    return embed_text_ids(model, tb["text_input_ids"], tb["text_mask"], batch_size)
+
+
+# ------------------------------------------------------------------------------------------------------- zero-shot
+@torch.no_grad()
+def zero_shot_logits(model: CACO, audio_embeddings: torch.Tensor, all_text_embeddings: torch.Tensor) -> torch.Tensor:
+    """eval_caco_torch.py:330: exp(logit_scale) * audio_embedding @ all_text_embeddings.T for all clips at once."""
+    at, _ = model.similarity(audio_embeddings, all_text_embeddings, want_ta=False)
+    return at
+
+
+@torch.no_grad()
+def zero_shot_topk(model: CACO, audio_embeddings: torch.Tensor, all_text_embeddings: torch.Tensor, k: int = 1) -> torch.Tensor:
+    """eval_caco_torch.py:330-331: argsort(-logits)[:, :k] as int32 [n_clips, k] (device)."""
+    return ops.topk_rows(zero_shot_logits(model, audio_embeddings, all_text_embeddings), k)
+
+
+@torch.no_grad()
+def zs_classification_arrays(model: CACO, all_text_embeddings: torch.Tensor, waves: Sequence[Any], target_indices: Sequence[int],
+                             datasetconfig: Optional[DatasetConfig] = None, ks: Sequence[int] = (1,), batch_size: int = 256
+                             ) -> Dict[str, float]:
+    """The loop body of zs_classification (eval_caco_torch.py:315-336) for in-memory clips: top-k accuracy per k."""
+    a = embed_waveforms(model, waves, datasetconfig, batch_size)
+    kmax = max(ks)
+    top = zero_shot_topk(model, a, all_text_embeddings, kmax)
+    tgt = torch.as_tensor(list(target_indices), dtype=torch.int32, device=top.device)[:, None]
+    out = {}
+    for k in ks:
+        out[str(k)] = float((top[:, :k] == tgt).any(dim=1).float().mean().item())
+    return out
+
+
+def zs_classification(model: CACO, tokenizer: Any, dataprocessor: Any, datasetconfig: DatasetConfig,
+                      device: Union[str, torch.device], subdir_name: str = "", text_prefix: str = "This is a sound of ") -> float:
+    """eval_caco_torch.py:289-340 (same arguments, same printed lines, same return value)."""
+    filepaths, descriptions, _ = dataprocessor.get_filepaths_and_descriptions(current_split=subdir_name)
+    class_labels = sorted(set(descriptions[a]["description"][0] for a in descriptions))
+    class_to_index_map = {v: i for i, v in enumerate(class_labels)}
+    all_text_embeddings = compute_all_class_embeddings(model, tokenizer, class_labels, datasetconfig.max_text_len, device,
+                                                       prefix=text_prefix)
+    waves, targets = [], []
+    for fp in filepaths:
+        audio_name = fp.split("/")[-1].split(".wav")[0]
+        targets.append(class_to_index_map[descriptions[audio_name]["description"][0]])
+        waves.append(loader.load_audio(fp, dataprocessor.config.sampling_rate, device).cpu())
+    acc = zs_classification_arrays(model, all_text_embeddings, waves, targets, datasetconfig, ks=(1,))
+    for k, v in acc.items():
+        print(f"top {k} accuracy: {v:.4f}")
+    return acc["1"]
+
+
+# ------------------------------------------------------------------------------------------------------- retrieval
+def jackknife_stats_mean(data: np.ndarray, confidence_level: float = 0.95) -> Tuple[float, float, float, np.ndarray]:
+    """``astropy.stats.jackknife_stats(data, np.mean, confidence_level)`` (called at eval_utils.py:57-66; astropy is a
+    third-party dependency of the reference, not vendored, restated from its documented algorithm): leave-one-out
+    resamples, bias = (n-1)(mean(resamples) - stat), std_err = sqrt((n-1) mean((resamples - mean(resamples))^2)),
+    estimate = stat - bias, interval = estimate ± z·std_err with z = sqrt(2)·erfinv(confidence_level).  For the mean
+    statistic the resamples have the closed form (sum - x_i)/(n-1), so no O(n^2) loop is needed."""
+    from scipy.special import erfinv
+    x = np.asarray(data, dtype=np.float64)
+    n = x.shape[0]
+    if n < 2:
+        raise ValueError("jackknife_stats_mean: at least two samples required")
+    stat = x.mean()
+    resamples = (x.sum() - x) / (n - 1)
+    mean_jack = resamples.mean()
+    bias = (n - 1) * (mean_jack - stat)
+    std_err = math.sqrt((n - 1) * np.mean((resamples - mean_jack) * (resamples - mean_jack)))
+    estimate = stat - bias
+    z = math.sqrt(2.0) * float(erfinv(confidence_level))
+    return float(estimate), float(bias), float(std_err), estimate + z * np.array((-std_err, std_err))
+
+
+def metrics_from_hit_bits(bits: np.ndarray) -> Dict[str, np.ndarray]:
+    """eval_utils.py:43-56 from the per-query hit masks (bit j = rank j+1 hit): per-query R1, R5, R10, AP@10 in float64."""
+    bits = np.asarray(bits, dtype=np.int64)
+    preds = ((bits[:, None] >> np.arange(10)[None, :]) & 1).astype(bool)              # [Q, 10]
+    r1 = preds[:, :1].any(axis=1).astype(np.float64)
+    r5 = preds[:, :5].any(axis=1).astype(np.float64)
+    r10 = preds[:, :10].any(axis=1).astype(np.float64)
+    ap = np.zeros(bits.shape[0], dtype=np.float64)
+    positions = np.arange(1, 11, dtype=np.float64)
+    for q in range(bits.shape[0]):                                                     # O(Q) host work, as in the reference
+        pos = positions[preds[q]]
+        if len(pos) > 0:
+            ap[q] = np.mean(np.arange(1, len(pos) + 1, dtype=np.float64) / pos, dtype=np.float64)
+    return {"R1": r1, "R5": r5, "R10": r10, "mAP10": ap}
+
+
+def _ids(names: Sequence[Any], table: Optional[Dict[Any, int]] = None) -> Tuple[np.ndarray, Dict[Any, int]]:
+    table = {} if table is None else table
+    out = np.empty(len(names), dtype=np.int32)
+    for i, n in enumerate(names):
+        out[i] = table.setdefault(n, len(table))
+    return out, table
+
+
+def compute_retrieval_metric(indices: Union[np.ndarray, torch.Tensor], all_querys: Sequence[Any], all_keys: Sequence[Any],
+                             gt_query_key: Dict[Any, Any], retrieval_type: str = "at", device: Union[str, torch.device] = "cuda",
+                             verbose: bool = True) -> Dict[str, Any]:
+    """eval_utils.py:18-66 (same arguments; prints the same four lines and also returns them).  `indices`: [queries, >= 10]
+    ranked key indices (numpy or a device tensor straight from ``ops.topk_rows``).  The per-query hit test runs on the
+    device (caco_retrieval_hits); names are mapped to integer ids on the host once."""
+    dev = torch.device(device)
+    top = torch.as_tensor(indices)[:, :10].to(device=dev, dtype=torch.int32).contiguous()
+    key_id, table = _ids(all_keys)
+    if retrieval_type == "ta":
+        gt = np.array([table.get(gt_query_key[q], -1) for q in all_querys], dtype=np.int32)        # unknown audio: never hit
+        bits = ops.retrieval_hits(top, torch.from_numpy(key_id).to(dev), torch.from_numpy(gt).to(dev))
+    elif retrieval_type == "at":
+        qid, qtable = _ids(all_querys)
+        n_key_ids = max(1, len(table))
+        pairs = set()
+        for q, g in qtable.items():
+            for key in gt_query_key[q]:
+                if key in table:
+                    pairs.add(int(g) * n_key_ids + table[key])
+        pairs_t = torch.tensor(sorted(pairs) or [-1], dtype=torch.int64, device=dev)
+        bits = ops.retrieval_hits(top, torch.from_numpy(key_id).to(dev), torch.from_numpy(qid).to(dev), pairs_t, n_key_ids)
+    else:
+        raise ValueError("retrieval_type must be 'at' or 'ta'")
+    per_query = metrics_from_hit_bits(bits.cpu().numpy())
+    out: Dict[str, Any] = {}
+    for name in ("R1", "R5", "R10", "mAP10"):
+        estimate, _, _, ci = jackknife_stats_mean(per_query[name], 0.95)
+        out[name] = (estimate, float(ci[0]), float(ci[1]))
+        if verbose:
+            print(name, f"{estimate:.3f}", f"[{ci[0]:.3f}, {ci[1]:.3f}]")
+    out["per_query"] = per_query
+    return out
+
+
+@torch.no_grad()
+def retrieval_topk(text_embeddings: torch.Tensor, audio_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+    """eval_caco_torch.py:396-406: logits_ar = T·Aᵀ; returns (argsort(-logits_arᵀ)[:, :k] — audio -> text,
+    argsort(-logits_ar)[:, :k] — text -> audio), int32 on the device.  Both products are computed directly (fp32 FMA)."""
+    ta = ops.sgemm_nt(text_embeddings.contiguous(), audio_embeddings.contiguous())          # [n_text, n_audio]
+    at = ops.sgemm_nt(audio_embeddings.contiguous(), text_embeddings.contiguous())          # [n_audio, n_text] = taᵀ
+    return ops.topk_rows(at, min(k, at.shape[1])), ops.topk_rows(ta, min(k, ta.shape[1]))
+
+
+@torch.no_grad()
+def audio_retrieval_arrays(model: CACO, waves: Sequence[Any], audio_names: Sequence[str], captions: Sequence[Sequence[str]],
+                           tokenizer: Any, datasetconfig: Optional[DatasetConfig] = None, verbose: bool = True) -> Dict[str, Any]:
+    """audio_retrieval (eval_caco_torch.py:343-408) for in-memory clips: captions[i] = the descriptions of clip i."""
+    cfg = datasetconfig or DatasetConfig()
+    dev = model._device()
+    all_text, gt_audio_text, gt_text_audio = [], {}, {}
+    for name, caps in zip(audio_names, captions):
+        gt_audio_text[name] = []
+        for c in caps:
+            gt_audio_text[name].append(c)
+            gt_text_audio[c] = name
+            all_text.append(c)
+    tb = prepare_text_batch(all_text, tokenizer, cfg.max_text_len, dev)
+    t = embed_text_ids(model, tb["text_input_ids"], tb["text_mask"])
+    a = embed_waveforms(model, waves, cfg)
+    at_idx, ta_idx = retrieval_topk(t, a, 10)
+    if at_idx.shape[1] < 10 or ta_idx.shape[1] < 10:
+        raise ValueError("audio_retrieval needs at least 10 clips and 10 captions (the reference indexes indices[i, :10])")
+    if verbose:
+        print("audio to text retrieval:")
+    res_at = compute_retrieval_metric(at_idx, list(audio_names), all_text, gt_audio_text, "at", dev, verbose)
+    if verbose:
+        print("text to audio retrieval:")
+    res_ta = compute_retrieval_metric(ta_idx, all_text, list(audio_names), gt_text_audio, "ta", dev, verbose)
+    return {"at": res_at, "ta": res_ta}
+
+
+def audio_retrieval(model: CACO, tokenizer: Any, dataprocessor: Any, datasetconfig: DatasetConfig,
+                    device: Union[str, torch.device], eval_split: str = "test") -> Dict[str, Any]:
+    """eval_caco_torch.py:343-408 (same arguments and printed output; additionally returns the metrics)."""
+    filepaths, descriptions, _ = dataprocessor.get_filepaths_and_descriptions(current_split=eval_split)
+    names, caps, waves = [], [], []
+    for fp in filepaths:
+        name = fp.split("/")[-1].split(".wav")[0]
+        names.append(name)
+        caps.append(list(descriptions[name]["description"]))
+        waves.append(loader.load_audio(fp, dataprocessor.config.sampling_rate, device).cpu())
+    return audio_retrieval_arrays(model, waves, names, caps, tokenizer, datasetconfig)

@@ -369,20 +369,40 @@ class CACO(nn.Module):
             return ops.sim_logits(a, t, self.logit_scale.data.reshape(1), want_ta=want_ta)
 
     @torch.no_grad()
-    def encode_audio(self, waveform: torch.Tensor, max_patches: int = 500, normalize: bool = True) -> torch.Tensor:
+    def encode_audio(self, waveform: torch.Tensor, max_patches: int = 500, normalize: bool = True,
+                     lengths: Optional[torch.Tensor] = None, return_hidden_state: bool = False,
+                     trim_padding: bool = False):
         """waveform [batch, n_samples] (16 kHz fp32) -> L2-normalised audio embeddings [batch, 768]:
-        prepare_audio_batch (eval_caco_torch.py:181-206) + get_audio_embedding in one library call."""
+        prepare_audio_batch (eval_caco_torch.py:181-206) + get_audio_embedding in one library call.
+
+        lengths [batch] (int): ragged batch — clip b is waveform[b, :lengths[b]], each clip framed / patched / masked as the
+        reference would treat it alone.  return_hidden_state: also return (hidden [batch, P, 768], mask [batch, P]).
+        trim_padding: run the tower on P = the largest valid-patch count in the batch (rounded up to 8) instead of
+        max_patches; masked keys get probability exactly 0 and padded tokens are never pooled, so the embeddings are the
+        same — only the padded rows of the hidden state are not produced (5 s clips: 248 instead of 500 tokens)."""
         h = self._ensure_packed()
         dev = self._device()
         w = _as(waveform, torch.float32, dev, "waveform")
         if w.dim() == 1:
             w = w[None]
         B, n = w.shape
+        lens = None
+        if lengths is not None:
+            lens = _as(torch.as_tensor(lengths), torch.int32, dev, "lengths")
+            if tuple(lens.shape) != (B,):
+                raise ValueError(f"lengths: expected shape {(B,)}")
+        P = int(max_patches)
+        if trim_padding:
+            longest = n if lengths is None else int(min(n, max(0, int(torch.as_tensor(lengths).max()))))
+            valid = (((longest + 159) // 160) // 16) * 8          # eval_caco_torch.py:67,116-117
+            P = max(8, min(P, valid))
         emb = torch.empty((B, self.audio_config.hidden_size), dtype=torch.float32, device=dev)
+        hid = torch.empty((B, P, self.audio_config.hidden_size), dtype=torch.float32, device=dev) if return_hidden_state else None
+        mk = torch.empty((B, P), dtype=torch.float32, device=dev) if return_hidden_state else None
         with torch.cuda.device(dev):
-            L.check(L.load().caco_model_encode_audio(h, L.ptr(w), B, n, max_patches, int(normalize), L.ptr(emb), L.stream_ptr()),
-                    "caco_model_encode_audio")
-        return emb
+            L.check(L.load().caco_model_encode_audio_ex(h, L.ptr(w), L.ptr(lens), B, n, P, int(normalize), L.ptr(emb),
+                                                        L.ptr(hid), L.ptr(mk), L.stream_ptr()), "caco_model_encode_audio_ex")
+        return (emb, hid, mk) if return_hidden_state else emb
 
     @torch.no_grad()
     def encode_text(self, text_input_ids: torch.Tensor, text_mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:

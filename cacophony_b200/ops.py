@@ -185,3 +185,68 @@ def frontend(wave: torch.Tensor, max_patches: int, want_log_mel: bool = False, w
     if want_f16:
         out["audio_patches_f16"] = p16
     return out
+
+
+def frontend_ragged(wave: torch.Tensor, lengths: torch.Tensor, max_patches: int, want_f16: bool = False):
+    """Ragged batch: wave [B, stride] fp32 (clip b = wave[b, :lengths[b]]), lengths [B] int32 CUDA -> the same dict as
+    `frontend`, every clip treated as eval_caco_torch.py:181-206 treats a single clip of its own length."""
+    _need(wave, torch.float32, "wave"); _need(lengths, torch.int32, "lengths")
+    if wave.dim() != 2 or lengths.dim() != 1 or lengths.shape[0] != wave.shape[0]:
+        raise ValueError("frontend_ragged: wave [batch, stride], lengths [batch] expected")
+    B, stride = wave.shape
+    dev = wave.device
+    patches = torch.empty((B, max_patches, 256), dtype=torch.float32, device=dev)
+    p16 = torch.empty((B, max_patches, 256), dtype=torch.float16, device=dev) if want_f16 else None
+    ti = torch.empty((B, max_patches), dtype=torch.float32, device=dev)
+    fi = torch.empty_like(ti)
+    mk = torch.empty_like(ti)
+    L.check(L.load().caco_frontend_ragged(L.ptr(wave), L.ptr(lengths), B, stride, max_patches, L.ptr(patches), L.ptr(p16),
+                                          L.ptr(ti), L.ptr(fi), L.ptr(mk), L.stream_ptr()), "caco_frontend_ragged")
+    out = {"audio_patches": patches, "audio_time_inds": ti, "audio_freq_inds": fi, "audio_mask": mk}
+    if want_f16:
+        out["audio_patches_f16"] = p16
+    return out
+
+
+def topk_rows(x: torch.Tensor, k: int, want_values: bool = False):
+    """argsort(-x, dim=-1)[:, :k] (ties: lower column first; NaN last) for x [rows, cols] fp32, k <= 32 -> int32 [rows, k]."""
+    _need(x, torch.float32, "x")
+    if x.dim() != 2:
+        raise ValueError("topk_rows: x must be [rows, cols]")
+    rows, cols = x.shape
+    if not (1 <= k <= 32 and k <= cols):
+        raise ValueError("topk_rows: need 1 <= k <= min(32, cols)")
+    idx = torch.empty((rows, k), dtype=torch.int32, device=x.device)
+    val = torch.empty((rows, k), dtype=torch.float32, device=x.device) if want_values else None
+    if rows:
+        L.check(L.load().caco_topk_rows(L.ptr(x), rows, cols, cols, k, L.ptr(idx), L.ptr(val), L.stream_ptr()), "caco_topk_rows")
+    return (idx, val) if want_values else idx
+
+
+def retrieval_hits(topk: torch.Tensor, key_id: torch.Tensor, gt_id: torch.Tensor, gt_pairs: Optional[torch.Tensor] = None,
+                   n_key_ids: int = 0) -> torch.Tensor:
+    """Hit bit-mask per query (bit j = rank j+1 is a hit), eval_utils.py:26-41.  gt_pairs None = 'ta' mode."""
+    _need(topk, torch.int32, "topk"); _need(key_id, torch.int32, "key_id"); _need(gt_id, torch.int32, "gt_id")
+    if topk.dim() != 2 or topk.shape[1] < 10:
+        raise ValueError("retrieval_hits: topk must be [queries, >= 10]")
+    Q = topk.shape[0]
+    if gt_id.numel() != Q:
+        raise ValueError("retrieval_hits: gt_id must have one entry per query")
+    mode = 0
+    if gt_pairs is not None:
+        _need(gt_pairs, torch.int64, "gt_pairs")
+        mode = 1
+    out = torch.empty((Q,), dtype=torch.int32, device=topk.device)
+    L.check(L.load().caco_retrieval_hits(L.ptr(topk), topk.shape[1], Q, L.ptr(key_id), L.ptr(gt_id), L.ptr(gt_pairs),
+                                         0 if gt_pairs is None else gt_pairs.numel(), int(n_key_ids), mode, L.ptr(out),
+                                         L.stream_ptr()), "caco_retrieval_hits")
+    return out
+
+
+def avg_pool_tokens(hid: torch.Tensor, group: int = 8) -> torch.Tensor:
+    """[B, S, D] -> [B, S // group, D] mean over groups of `group` consecutive tokens (caco_embeddings.py:124-125)."""
+    _need(hid, torch.float32, "hid")
+    B, S, D = hid.shape
+    out = torch.empty((B, S // group, D), dtype=torch.float32, device=hid.device)
+    L.check(L.load().caco_avg_pool_tokens(L.ptr(hid), B, S, D, group, L.ptr(out), L.stream_ptr()), "caco_avg_pool_tokens")
+    return out

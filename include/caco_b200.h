@@ -52,6 +52,12 @@ int caco_built_arch(void);
 int caco_frontend(const float* wave, int batch, int n_samples, int max_patches, float* patches, void* patches_f16,
                   float* time_inds, float* freq_inds, float* mask, float* log_mel, void* stream);
 
+/* Ragged batch: clip b = wave[b*stride : b*stride + lengths[b]], lengths = DEVICE int32 [batch].  Each
+ * clip gets eval_caco_torch.py:181-206's per-clip treatment (own frame count ceil(L/160), own valid-patch count
+ * floor(frames/16)*8 truncated to max_patches, zero padding rows, mask) in one launch. */
+int caco_frontend_ragged(const float* wave, const int* lengths, int batch, int stride, int max_patches, float* patches,
+                         void* patches_f16, float* time_inds, float* freq_inds, float* mask, void* stream);
+
 /* ---- K2: out = epilogue(A[M,K] f16 · W[N,K]ᵀ f16), fp32 accumulate on tcgen05 tensor cores.
  * Replaces every nn.Linear on the path (mae.py:51-52,69,116; roberta.py:62-64,110,153,164; caco.py:35,37).
  * lda/ldw/ldo/ldr are leading dimensions in ELEMENTS.  N % 4 == 0, K % 8 == 0.                       */
@@ -124,6 +130,20 @@ int caco_l2norm(const float* in, float* out, int rows, int dim, float eps, void*
 int caco_sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt,
                     int dim, void* stream);
 
+/* ---- row (f-2): the device side of the evaluation drivers (eval_caco_torch.py:289-408, eval_utils.py:18-66).
+ * caco_topk_rows: idx_out[r, :k] = argsort(-x[r, :])[:k] (ties: lower column first, NaN last), k <= 32; val_out may be NULL.
+ * Replaces torch.argsort(-logits, dim=-1) at eval_caco_torch.py:331,401,406 (only the first k <= 10 ranks are ever used). */
+int caco_topk_rows(const float* x, int rows, int cols, int ldx, int k, int* idx_out, float* val_out, void* stream);
+/* caco_retrieval_hits: `preds` of compute_retrieval_metric (eval_utils.py:26-41) for every query: out[q] bit j = rank j+1 hit.
+ * topk [n_queries, ldk >= 10] int32 key indices; key_id [n_keys] int32; gt_id [n_queries] int32.
+ * mode 0 ('ta'): hit = key_id[idx] == gt_id[q].   mode 1 ('at'): hit = (gt_id[q] * n_key_ids + key_id[idx]) is in the sorted
+ * int64 array gt_pairs AND that key_id was not already counted at an earlier rank. */
+int caco_retrieval_hits(const int* topk, int ldk, int n_queries, const int* key_id, const int* gt_id,
+                        const long long* gt_pairs, int n_pairs, long long n_key_ids, int mode, int* out, void* stream);
+/* ---- row (f-4): HEAR timestamp embeddings (caco_embeddings.py:124-129): out[b, t, :] = mean of hid[b, t*group .. +group-1, :],
+ * t < seq / group ('VALID'). */
+int caco_avg_pool_tokens(const float* hid, int batch, int seq, int dim, int group, float* out, void* stream);
+
 /* ======================================= model handle ==========================================
  * A handle owns fp16-packed copies of the encoder weights, folded pooler vectors and an activation
  * workspace (cudaMalloc); inputs/outputs stay caller-owned.  Mirrors CACO (src/caco_torch/caco.py:82-261). */
@@ -163,6 +183,12 @@ int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* ma
 /* waveform-in convenience: frontend + get_audio_embedding in one call (encode_audio). */
 int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
                             float* emb_out, void* stream);
+/* general form: lengths (DEVICE int32 [batch]) or NULL for a uniform batch of `stride` samples; hidden_out
+ * [batch, max_patches, hidden] f32 (the LayerNorm-ed encoder output, what HEAR timestamp embeddings pool) or NULL;
+ * mask_out [batch, max_patches] f32 or NULL. */
+int caco_model_encode_audio_ex(caco_model* m, const float* wave, const int* lengths, int batch, int stride,
+                               int max_patches, int normalize, float* emb_out, float* hidden_out, float* mask_out,
+                               void* stream);
 /* DEVICE pointer to the registered logit_scale scalar (caco.py:116), for caco_sim_logits. */
 const float* caco_model_logit_scale(caco_model* m);
 /* number of kernels the library has launched since load (bench.py's gpu_launches). */

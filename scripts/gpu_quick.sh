@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python scripts/ab_step.py red=caco_set_gemm_resid_red:1 nored=caco_set_gemm_resid_red:0 e8=caco_set_gemm_variant:3 auto=caco_set_gemm_variant:0 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_eval_gpu.py -x -q > gpurun_out/pytest_eval.log 2>&1; echo "pytest eval rc=$?"; tail -40 gpurun_out/pytest_eval.log

@@ -1,0 +1,99 @@
+"""CPU: the evaluation-side oracle (oracle/eval_oracle.py) against the golden arrays produced by the reference's own
+compute_retrieval_metric (tests/golden/eval_retrieval.npz, generator oracle/make_golden_eval.py), and the host-side logic
+of the batched drivers (packing, metric arithmetic, jackknife closed form)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cacophony_b200 import eval as ev
+from cacophony_b200 import loader
+from oracle import eval_oracle as E
+from oracle.make_golden_eval import CASES
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_retrieval_matches_reference_golden(case, golden_dir):
+    name, seed, n_audio, caps, dup = case
+    g = np.load(os.path.join(golden_dir, "eval_retrieval.npz"))
+    names, all_text, gt_at, gt_ta, at_idx, ta_idx = E.make_retrieval_case(seed, n_audio, caps, dup)
+    for kind, idx, qs, ks, gt in (("at", at_idx, names, all_text, gt_at), ("ta", ta_idx, all_text, names, gt_ta)):
+        per_query = E.retrieval_per_query(E.retrieval_preds(idx, qs, ks, gt, kind))
+        for metric in ("R1", "R5", "R10", "mAP10"):
+            ref = g[f"{name}/{kind}/{metric}"]
+            assert np.array_equal(per_query[metric], ref), (name, kind, metric)      # float64, bit-exact
+        assert per_query["R10"].sum() > 0                                             # the cases do contain hits
+
+
+def test_metrics_from_hit_bits_equals_oracle():
+    rng = np.random.default_rng(3)
+    preds = rng.random((500, 10)) < 0.2
+    preds[0] = False
+    preds[1] = True
+    bits = (preds.astype(np.int64) << np.arange(10)[None, :]).sum(axis=1)
+    got = ev.metrics_from_hit_bits(bits)
+    ref = E.retrieval_per_query(preds)
+    for k in ref:
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_jackknife_closed_form_equals_leave_one_out():
+    rng = np.random.default_rng(5)
+    for data in (rng.random(57), (rng.random(200) < 0.3).astype(float), np.array([0.0, 1.0])):
+        est, bias, se, ci = ev.jackknife_stats_mean(data, 0.95)
+        r_est, r_bias, r_se, r_ci = E.jackknife_stats(data, np.mean, 0.95)
+        np.testing.assert_allclose([est, se, ci[0], ci[1]], [r_est, r_se, r_ci[0], r_ci[1]], rtol=1e-10, atol=1e-12)
+        assert abs(bias - r_bias) < 1e-12
+    # known answer: for the mean, std_err is the usual standard error of the mean and z(0.95) = 1.959964
+    x = np.arange(10, dtype=float)
+    est, _, se, ci = ev.jackknife_stats_mean(x)
+    assert abs(est - 4.5) < 1e-12 and abs(se - x.std(ddof=1) / np.sqrt(10)) < 1e-12
+    assert abs((ci[1] - est) / se - 1.959963984540054) < 1e-9
+
+
+def test_oracle_topk_is_argsort_of_negated_scores():
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((40, 300)).astype(np.float32)
+    ref = torch.argsort(-torch.from_numpy(x), dim=-1, stable=True)[:, :10].numpy()
+    assert np.array_equal(E.topk_indices(x, 10), ref)
+    x[:, 5] = x[:, 200]                                  # ties resolve to the lower column
+    top = E.topk_indices(x, 300)
+    pos5 = np.argmax(top == 5, axis=1)
+    pos200 = np.argmax(top == 200, axis=1)
+    assert (pos5 + 1 == pos200).all()
+    x[3, 7] = np.nan
+    assert E.topk_indices(x, 300)[3, -1] == 7            # NaN ranks last
+
+
+def test_pad_ragged_and_valid_counts():
+    waves = [np.arange(5, dtype=np.float32), torch.ones(330), np.ones((200, 2), dtype=np.float64) * [1.0, 3.0]]
+    buf, lens = loader.pad_ragged(waves, pin=False)
+    assert buf.shape == (3, 480) and buf.dtype == torch.float32 and lens.tolist() == [5, 330, 200]
+    assert buf[0, :5].tolist() == [0, 1, 2, 3, 4] and float(buf[0, 5:].abs().sum()) == 0
+    assert float(buf[2, :200].mean()) == 2.0 and float(buf[2, 200:].abs().sum()) == 0      # channel mean
+    buf2, lens2 = loader.pad_ragged(waves, stride=100, pin=False)
+    assert buf2.shape == (3, 100) and lens2.tolist() == [5, 100, 100]
+    # eval_caco_torch.py:67,116-117,132-138
+    assert loader.valid_patch_counts([160000, 80000, 159999, 12345, 100, 192000], 500).tolist() == [496, 248, 496, 32, 0, 500]
+    with pytest.raises(ValueError):
+        loader.pad_ragged([])
+
+
+def test_drivers_refuse_cpu_and_missing_tokenizer():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loader.prepare_audio_batch_ragged([np.zeros(16000, np.float32)], device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loader.resample_to_16k(np.zeros(100, np.float32), 44100, device="cpu")
+    with pytest.raises(ValueError, match="tokenizer"):
+        ev.prepare_text_batch("a dog barks", None, 100, "cpu")
+
+
+def test_load_caco_torch_accepts_the_reference_checkpoint_layouts():
+    from oracle import weights as W
+    sd = {n: torch.zeros(s) for n, s, _ in W.param_spec()}
+    sd["decoder_module.layers.0.output.dense.bias"] = torch.zeros(768)            # captioning head: ignored
+    for wrap in (lambda d: d, lambda d: {"state_dict": d}, lambda d: {"model_state_dict": d, "epoch": 3}):
+        out = ev.load_caco_torch(None, "cpu", tokenizer="tok", state_dict=wrap(sd))
+        assert set(out) == {"model", "tokenizer", "device"} and out["tokenizer"] == "tok"
+        assert not out["model"].training
