@@ -31,6 +31,37 @@ if rank == 0:
     d2 = (ta[lo:hi] - ta_blk).abs().max().item()
     ok = d1 < 1e-4 and d2 < 1e-4 and tuple(at_blk.shape) == (hi - lo, B)
     print(f"sharded vs single-GPU: max|d at| = {d1:.2e}, max|d ta| = {d2:.2e}, block {tuple(at_blk.shape)} -> {'OK' if ok else 'FAIL'}")
+
+# ---- config #5 shape (scaled down): 5 s clips sharded, class prompts (T = 100) replicated, predictions gathered
+import numpy as np
+from cacophony_b200 import eval as ev
+from cacophony_b200 import ops
+g = torch.Generator().manual_seed(5)
+n_clips, n_cls = 6 * world + 1, 50                     # uneven shard on purpose
+clips = [(0.1 * (2 * torch.rand(80000, generator=g) - 1)).numpy() for _ in range(n_clips)]
+cls_ids = torch.randint(3, 50265, (n_cls, 100), generator=g)
+cls_mask = torch.zeros(n_cls, 100, dtype=torch.int64)
+for i in range(n_cls):
+    n = 8 + i % 5
+    cls_ids[i, 0], cls_ids[i, n - 1], cls_ids[i, n:] = 0, 2, 1
+    cls_mask[i, :n] = 1
+t_cls = ev.embed_text_ids(model, cls_ids.cuda(), cls_mask.cuda())
+top = cdist.sharded_zero_shot_topk(model, clips, t_cls, k=1)
+a_full = ev.embed_waveforms(model, clips)
+ref_top = ev.zero_shot_topk(model, a_full, t_cls, 1)
+ok5 = tuple(top.shape) == (n_clips, 1) and torch.equal(top, ref_top)
+# ---- sharded retrieval rankings == single-GPU rankings
+lo_a, hi_a = cdist.shard_range(n_clips, rank, world)
+lo_t, hi_t = cdist.shard_range(n_cls, rank, world)
+at_idx, ta_idx = cdist.sharded_retrieval_topk(model, a_full[lo_a:hi_a].contiguous(), t_cls[lo_t:hi_t].contiguous(), n_clips, n_cls, 10)
+ref_at, ref_ta = ev.retrieval_topk(t_cls, a_full, 10)
+okr = torch.equal(at_idx, ref_at) and torch.equal(ta_idx, ref_ta)
+flag = torch.tensor([int(ok5), int(okr)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"config-5 sharded zero-shot top-1 ({n_clips} clips x {n_cls} prompts over {world} ranks) == single GPU: {bool(flag[0])}; "
+          f"sharded retrieval rankings == single GPU: {bool(flag[1])}")
+ok = ok and bool(flag[0]) and bool(flag[1])
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -48,6 +48,11 @@ def _worker(rank, world, port, q):
         at_blk, ta_blk = cdist.sharded_contrastive_logits(_FakeModel(), a_all[lo:hi].contiguous(), t_all[lo:hi].contiguous())
         full_at, full_ta = _FakeModel().similarity(a_all, t_all)
         ok = ok and torch.allclose(at_blk, full_at[lo:hi], atol=1e-6) and torch.allclose(ta_blk, full_ta[lo:hi], atol=1e-6)
+        # uneven row blocks (config #5: 400 clips over 8 ranks is even, 50 prompts / 7 clips are not)
+        for n_total in (7, 2, 1, 10):
+            full = torch.arange(n_total * 3, dtype=torch.int32).reshape(n_total, 3)
+            rlo, rhi = cdist.shard_range(n_total, rank, world)
+            ok = ok and torch.equal(cdist.gather_rows(full[rlo:rhi].contiguous(), n_total), full)
         q.put((rank, bool(ok)))
     except Exception as e:          # surface the failure instead of letting the parent time out
         q.put((rank, repr(e)))
