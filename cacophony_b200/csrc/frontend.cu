@@ -99,17 +99,67 @@ static int frontend_init() {
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_negi(float2 a) { return make_float2(a.y, -a.x); }   // -i * a
 
+// 4-point forward DFT in place: (a, b, c, d) -> (X0, X1, X2, X3)
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_negi(csub(b, d));
+  a = cadd(s0, s2);
+  b = cadd(s1, s3);
+  c = csub(s0, s2);
+  d = csub(s1, s3);
+}
+
+// 16-point forward DFT of v[0..15] in registers, natural order in and out: n = 4a + b, k = c + 4d,
+// X[c + 4d] = sum_b W16^{bc} W4^{bd} sum_a v[4a + b] W4^{ac}  (two radix-4 stages, compile-time twiddles)
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128673848f, S1 = 0.38268343236508978178f, R2 = 0.70710678118654752440f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);      // v[4c + b] = u_b[c]
+  // u_b[c] *= W16^{bc}
+  v[4 + 1] = cmul(v[4 + 1], make_float2(C1, -S1));     // b=1,c=1: W^1
+  v[8 + 1] = cmul(v[8 + 1], make_float2(R2, -R2));     // b=1,c=2: W^2
+  v[12 + 1] = cmul(v[12 + 1], make_float2(S1, -C1));   // b=1,c=3: W^3
+  v[4 + 2] = cmul(v[4 + 2], make_float2(R2, -R2));     // b=2,c=1: W^2
+  v[8 + 2] = mul_negi(v[8 + 2]);                       // b=2,c=2: W^4 = -i
+  v[12 + 2] = cmul(v[12 + 2], make_float2(-R2, -R2));  // b=2,c=3: W^6
+  v[4 + 3] = cmul(v[4 + 3], make_float2(S1, -C1));     // b=3,c=1: W^3
+  v[8 + 3] = cmul(v[8 + 3], make_float2(-R2, -R2));    // b=3,c=2: W^6
+  v[12 + 3] = cmul(v[12 + 3], make_float2(-C1, S1));   // b=3,c=3: W^9
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);   // v[4c + d] = X[c + 4d]
+  // transpose the 4x4 index so that v[k] = X[k]
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int d = c + 1; d < 4; ++d) {
+      const float2 t = v[4 * c + d];
+      v[4 * c + d] = v[4 * d + c];
+      v[4 * d + c] = t;
+    }
+}
+
+constexpr int FE_ZLD = 17;                               // padded row of the 16x16 exchange buffer (float2 units)
+constexpr int FE_ZFRAME = 16 * FE_ZLD;                   // 272 float2 per frame (>= 257 floats for the magnitudes)
+constexpr int FE_SMEM_BYTES = FE_SAMPLES * 4 + FE_FRAMES * FE_ZFRAME * 8 + 256 * 8 + 1024;   // samples, exchange, W256 table
+
+// 16 threads per frame, 16 frames per CTA.  The 512-point real FFT of a frame is a 256-point complex FFT of
+// z[n] = x[2n] + i x[2n+1], done as 16 x 16: thread n2 transforms z[16 n1 + n2] over n1 in registers, multiplies by
+// W256^{n2 k1}, the frame's 16 threads exchange through one padded (conflict-free) shared-memory tile, thread k1 transforms
+// over n2 and owns X[k1 + 16 k2]; the conjugate partner Z[256 - k] for the real split comes from a second pass through the
+// same tile.  Two shared-memory round trips per frame instead of the eight of a radix-4 Stockham, and only warp-level
+// synchronisation (a frame lives in half a warp).
 __global__ void __launch_bounds__(256)
 frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths, int stride, int n_samples_u, int max_patches,
                 float* __restrict__ patches, __half* __restrict__ patches_f16, float* __restrict__ time_inds,
                 float* __restrict__ freq_inds, float* __restrict__ mask, float* __restrict__ log_mel) {
-  __shared__ float s_x[FE_SAMPLES];
-  __shared__ float2 s_tw[FE_NFFT];                 // e^{-2 pi i k / 512}
-  __shared__ float s_win[FE_WIN];
-  __shared__ float2 s_buf[2][4][256];              // ping-pong, 4 frames in flight
-  __shared__ float s_mag[4][FE_NFREQ + 3];
-  __shared__ float s_out[FE_FRAMES][FE_MEL_LD];
+  extern __shared__ __align__(16) uint8_t fe_smem[];
+  float* s_x = reinterpret_cast<float*>(fe_smem);                                   // 2912 samples; later the log-mel tile
+  float2* s_z = reinterpret_cast<float2*>(fe_smem + FE_SAMPLES * 4);                // [16 frames][16][17]
+  float2* s_w256 = reinterpret_cast<float2*>(fe_smem + FE_SAMPLES * 4 + FE_FRAMES * FE_ZFRAME * 8);   // [k1][n2] = W256^{n2 k1}
+  float (*s_out)[FE_MEL_LD] = reinterpret_cast<float (*)[FE_MEL_LD]>(s_x);          // [16][144] = 2304 floats <= 2912
 
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   // ragged batches: clip b holds lengths[b] samples in a row of `stride` floats (uniform batches: lengths == nullptr)
@@ -152,80 +202,85 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     return;
   }
 
-  // ---- stage samples (zero tail pad, eval_caco_torch.py:72-78), twiddles, window, mel table
+  // ---- stage samples (zero tail pad, eval_caco_torch.py:72-78) and the W256 table (transposed: [k1][n2])
   const float* wv = wave + (size_t)b * stride;
   const int s0 = frame0 * FE_HOP;
   for (int i = tid; i < FE_SAMPLES; i += 256) {
     const int s = s0 + i;
     s_x[i] = (s < n_samples) ? __ldg(wv + s) : 0.0f;
   }
-  for (int i = tid; i < FE_NFFT; i += 256) s_tw[i] = g_twiddle[i];
-  for (int i = tid; i < FE_WIN; i += 256) s_win[i] = g_window[i];
+  {
+    const int k1 = tid >> 4, n2 = tid & 15;
+    s_w256[tid] = g_twiddle[(2 * n2 * k1) & 511];          // W256^m = W512^{2m}
+  }
   __syncthreads();
 
-  const int slot = tid >> 6;  // frame slot 0..3
-  const int j = tid & 63;     // radix-4 butterfly index
-  for (int round = 0; round < FE_FRAMES / 4; ++round) {
-    const int dt = round * 4 + slot;
-    const float* xf = s_x + dt * FE_HOP;
-    int cur = 0;
+  const int fr = tid >> 4;       // frame within the CTA
+  const int q = tid & 15;        // n2 in pass 1, k1 in pass 2
+  float2* zf = s_z + fr * FE_ZFRAME;
+  float2 v[16];
+  {
+    // z[16 n1 + q] = (x[2n] w[2n], x[2n+1] w[2n+1]), n = 16 n1 + q; window support is [56, 456) of the 512-sample frame
+    const float* xf = s_x + fr * FE_HOP;
 #pragma unroll
-    for (int stage = 0; stage < 4; ++stage) {
-      const int Ns = 1 << (2 * stage);
-      float2 v[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = j + r * 64;
-        if (stage == 0) {
-          // z[n] = xw[2n] + i xw[2n+1], window support is [56, 456)
-          const int i0 = 2 * n, i1 = 2 * n + 1;
-          const float w0 = (i0 >= FE_WOFF && i0 < FE_WOFF + FE_WIN) ? s_win[i0 - FE_WOFF] : 0.0f;
-          const float w1 = (i1 >= FE_WOFF && i1 < FE_WOFF + FE_WIN) ? s_win[i1 - FE_WOFF] : 0.0f;
-          v[r] = make_float2(xf[i0] * w0, xf[i1] * w1);
-        } else {
-          v[r] = s_buf[cur][slot][n];
-          if (r > 0) v[r] = cmul(v[r], s_tw[((j & (Ns - 1)) * r * (128 / Ns)) & 511]);
-        }
-      }
-      const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-      const float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-      const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-      const float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-      const float2 a3 = make_float2(d.y, -d.x);  // -i * d
-      const int idx = (j / Ns) * Ns * 4 + (j & (Ns - 1));
-      float2* dst = s_buf[stage == 0 ? 0 : (cur ^ 1)][slot];
-      dst[idx] = make_float2(a0.x + a2.x, a0.y + a2.y);
-      dst[idx + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-      dst[idx + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-      dst[idx + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
-      if (stage > 0) cur ^= 1;
-      named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int i0 = 2 * (16 * n1 + q), i1 = i0 + 1;
+      const float w0 = (i0 >= FE_WOFF && i0 < FE_WOFF + FE_WIN) ? __ldg(g_window + i0 - FE_WOFF) : 0.0f;
+      const float w1 = (i1 >= FE_WOFF && i1 < FE_WOFF + FE_WIN) ? __ldg(g_window + i1 - FE_WOFF) : 0.0f;
+      const float2 xx = *reinterpret_cast<const float2*>(xf + i0);
+      v[n1] = make_float2(xx.x * w0, xx.y * w1);
     }
-    // ---- real split: X[k] = E + W^k O, |X[k]|, k = 0..256
-    const float2* Z = s_buf[cur][slot];
-    for (int k = j; k <= 256; k += 64) {
-      const float2 zk = Z[k & 255];
-      const float2 zc = Z[(256 - k) & 255];
-      const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);      // E = (Zk + conj Zc)/2
-      const float dr = zk.x - zc.x, di = zk.y + zc.y;                        // Zk - conj Zc
-      const float orr = 0.5f * di, oi = -0.5f * dr;                          // O = -i/2 (Zk - conj Zc)
-      const float2 w = (k < 256) ? s_tw[k] : make_float2(-1.0f, 0.0f);
-      const float xr = er + (w.x * orr - w.y * oi);
-      const float xi = ei + (w.x * oi + w.y * orr);
-      s_mag[slot][k] = sqrtf(xr * xr + xi * xi);
-    }
-    named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
-    // ---- sparse mel + log (eval_caco_torch.py:103-104)
-    for (int m = j; m < FE_NMEL; m += 64) {
-      const int st = g_mel.start[m], cnt = g_mel.count[m];  // 9 KB table, L1/L2 resident
-      float acc = 0.0f;
-      for (int q = 0; q < cnt; ++q) acc = fmaf(s_mag[slot][st + q], g_mel.w[m][q], acc);
-      s_out[dt][m] = logf(acc + 1e-5f) * 0.2f + 0.9f;
-    }
-    named_bar_sync(1 + slot, 64);   // only the two warps working on this frame
   }
-
-  __syncthreads();   // all four 64-thread groups have filled their rows of s_out
+  dft16(v);                                                 // over n1 -> index k1
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], s_w256[k1 * 16 + q]);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) zf[k1 * FE_ZLD + q] = v[k1];
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = zf[q * FE_ZLD + n2];
+  dft16(v);                                                 // over n2 -> v[k2] = Z[q + 16 k2]
+  __syncwarp();
+  // second exchange: natural order Z[k] so that every thread can fetch the conjugate partners Z[256 - k]
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) zf[q + 16 * k2] = v[k2];
+  __syncwarp();
+  float mag[16];
+  float mag_nyq = 0.0f;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    // real split: X[k] = E + W512^k O,  E = (Z[k] + conj Z[256-k]) / 2,  O = -i (Z[k] - conj Z[256-k]) / 2
+    const int k = q + 16 * k2;
+    const float2 zk = v[k2];
+    const float2 zc = zf[(256 - k) & 255];
+    const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
+    const float dr = zk.x - zc.x, di = zk.y + zc.y;
+    const float orr = 0.5f * di, oi = -0.5f * dr;
+    const float2 w = g_twiddle[k];
+    const float xr = er + (w.x * orr - w.y * oi);
+    const float xi = ei + (w.x * oi + w.y * orr);
+    mag[k2] = sqrtf(xr * xr + xi * xi);
+    if (k == 0) {                                           // X[256] = E - O at k = 0 (W512^256 = -1)
+      const float nr = er - orr, ni = ei - oi;
+      mag_nyq = sqrtf(nr * nr + ni * ni);
+    }
+  }
+  __syncwarp();                                             // every partner read is done: the tile becomes the magnitudes
+  float* s_mag = reinterpret_cast<float*>(zf);              // [257]
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) s_mag[q + 16 * k2] = mag[k2];
+  if (q == 0) s_mag[256] = mag_nyq;
+  __syncthreads();                                          // all frames have consumed s_x: it becomes the log-mel tile
+  // ---- sparse mel + log (eval_caco_torch.py:103-104): 8 filters per thread
+#pragma unroll
+  for (int i = 0; i < FE_NMEL / 16; ++i) {
+    const int m = q + 16 * i;
+    const int st = g_mel.start[m], cnt = g_mel.count[m];   // 9 KB table, L1/L2 resident
+    float acc = 0.0f;
+    for (int c = 0; c < cnt; ++c) acc = fmaf(s_mag[st + c], g_mel.w[m][c], acc);
+    s_out[fr][m] = logf(acc + 1e-5f) * 0.2f + 0.9f;
+  }
+  __syncthreads();
   // ---- optional raw log-mel [B, n_frames, 128]
   if (log_mel != nullptr) {
     for (int i = tid; i < FE_FRAMES * FE_NMEL; i += 256) {
@@ -239,10 +294,10 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
       const int f = i >> 8, e = i & 255;
       const int p = t * 8 + f;
       if (p < max_patches) {
-        const float v = s_out[e >> 4][16 * f + (e & 15)];
+        const float val = s_out[e >> 4][16 * f + (e & 15)];
         const size_t o = ((size_t)b * max_patches + p) * 256 + e;
-        if (patches) patches[o] = v;
-        if (patches_f16) patches_f16[o] = __float2half_rn(v);
+        if (patches) patches[o] = val;
+        if (patches_f16) patches_f16[o] = __float2half_rn(val);
       }
     }
   } else if (t < T_out) {
@@ -269,7 +324,13 @@ int frontend(const float* wave, const int* lengths, int batch, int n_samples, in
   int gx = T_out;
   if (log_mel != nullptr) gx = max(gx, (n_frames + FE_FRAMES - 1) / FE_FRAMES);
   dim3 grid(gx, batch);
-  frontend_kernel<<<grid, 256, 0, stream>>>(wave, lengths, n_samples, n_samples, max_patches, patches,
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  frontend_kernel<<<grid, 256, FE_SMEM_BYTES, stream>>>(wave, lengths, n_samples, n_samples, max_patches, patches,
                                             reinterpret_cast<__half*>(patches_f16), time_inds, freq_inds, mask, log_mel);
   count_launch();
   return (int)cudaGetLastError();
