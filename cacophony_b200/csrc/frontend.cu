@@ -2,11 +2,12 @@
 // Replaces compute_mel_spectrogram + spectrogram_to_patches + prepare_audio_batch
 // (src/eval/eval_caco_torch.py:41-105, :108-151, :181-206), batched and without the host numpy hop.
 //
-// One CTA per (clip, 16-frame group) = one patch row t: it stages the 2912 samples the 16 frames touch,
-// runs 16 real 512-point FFTs in shared memory (256-point complex radix-4 Stockham + real split, fp32,
-// host-computed twiddle table), applies the sparse HTK filterbank (505 non-zeros), log(x+1e-5)*0.2+0.9, and
-// writes the 8 patches of that row — 8 KB contiguous in the [B, max_patches, 256] layout — with
-// coalesced 128-byte stores.  HBM-bound by design: 1.158 MB per 10 s clip.
+// One CTA per (clip, 16-frame group) = one patch row t: it stages the 2912 samples the 16 frames touch and the constant
+// tables with cp.async, runs 16 real 512-point FFTs (each a 256-point complex FFT done as two radix-16 passes in the
+// registers of 16 threads, one padded shared-memory exchange between them, fp32, host-computed twiddles) + real split,
+// applies the sparse HTK filterbank (505 non-zeros), log(x+1e-5)*0.2+0.9, and writes the 8 patches of that row — 8 KB
+// contiguous in the [B, max_patches, 256] layout — with coalesced 128-byte stores.  Algorithmic HBM traffic: 1.158 MB per
+// 10 s clip.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -27,14 +28,18 @@ constexpr int FE_FRAMES = 16;                    // frames per CTA (= patch heig
 constexpr int FE_SAMPLES = (FE_FRAMES - 1) * FE_HOP + FE_NFFT;  // 2912
 constexpr int FE_MEL_LD = 144;                   // padded row of the staged log-mel tile
 
-struct MelTable {
-  int start[FE_NMEL];
-  int count[FE_NMEL];
-  float w[FE_NMEL][FE_MAXW];
+// Constant tables, packed so that every CTA pulls them into shared memory with 16-byte cp.async copies (9.3 KB):
+struct FeTables {
+  float2 w256t[256];        // [k1][n2] = e^{-2 pi i n2 k1 / 256}: twiddles between the two radix-16 passes
+  float2 w512[256];         // e^{-2 pi i k / 512}, k < 256: real-split twiddles (computed in double on the host)
+  float win[FE_WIN];        // periodic Hann(400)
+  int mel_start[FE_NMEL];   // first FFT bin of each HTK filter
+  int mel_count[FE_NMEL];   // number of non-zero taps (<= FE_MAXW)
+  int mel_woff[FE_NMEL];    // offset of the filter's taps in mel_w
+  float mel_w[512];         // the 505 non-zero filterbank weights, filter after filter
 };
-__device__ MelTable g_mel;
-__device__ float2 g_twiddle[FE_NFFT];   // e^{-2 pi i k / 512}, computed in double on the host
-__device__ float g_window[FE_WIN];      // periodic Hann(400)
+static_assert(sizeof(FeTables) % 16 == 0, "tables are copied in 16-byte pieces");
+__device__ __align__(16) FeTables g_fe;
 
 // torch.linspace(start, end, steps) in fp32: symmetric evaluation from both ends.
 static void linspace_f32(float start, float end, int steps, std::vector<float>& out) {
@@ -70,33 +75,44 @@ static int frontend_init() {
   std::call_once(once, [] {
     std::vector<float> fb(FE_NFREQ * FE_NMEL);
     mel_filterbank_host(fb.data());
-    MelTable t;
+    static FeTables t;
     rc = 0;
+    int woff = 0;
     for (int m = 0; m < FE_NMEL; ++m) {
       int lo = -1, hi = -1;
       for (int k = 0; k < FE_NFREQ; ++k)
         if (fb[k * FE_NMEL + m] != 0.0f) { if (lo < 0) lo = k; hi = k; }
-      t.start[m] = lo < 0 ? 0 : lo;
-      t.count[m] = lo < 0 ? 0 : hi - lo + 1;
-      if (t.count[m] > FE_MAXW) { rc = CACO_ERR_STATE; return; }
-      for (int j = 0; j < FE_MAXW; ++j) t.w[m][j] = (j < t.count[m]) ? fb[(t.start[m] + j) * FE_NMEL + m] : 0.0f;
+      t.mel_start[m] = lo < 0 ? 0 : lo;
+      t.mel_count[m] = lo < 0 ? 0 : hi - lo + 1;
+      t.mel_woff[m] = woff;
+      if (t.mel_count[m] > FE_MAXW || woff + t.mel_count[m] > 512) { rc = CACO_ERR_STATE; return; }
+      for (int j = 0; j < t.mel_count[m]; ++j) t.mel_w[woff++] = fb[(t.mel_start[m] + j) * FE_NMEL + m];
     }
-    cudaError_t e = cudaMemcpyToSymbol(g_mel, &t, sizeof(t));
-    if (e != cudaSuccess) { rc = (int)e; return; }
-    std::vector<float2> tw(FE_NFFT);
-    for (int k = 0; k < FE_NFFT; ++k) {
+    for (; woff < 512; ++woff) t.mel_w[woff] = 0.0f;
+    for (int k = 0; k < 256; ++k) {
       const double ang = -2.0 * M_PI * (double)k / (double)FE_NFFT;
-      tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+      t.w512[k] = make_float2((float)cos(ang), (float)sin(ang));
     }
-    e = cudaMemcpyToSymbol(g_twiddle, tw.data(), sizeof(float2) * FE_NFFT);
-    if (e != cudaSuccess) { rc = (int)e; return; }
-    std::vector<float> win(FE_WIN);
-    for (int i = 0; i < FE_WIN; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)FE_WIN));   // torch.hann_window(400)
-    e = cudaMemcpyToSymbol(g_window, win.data(), sizeof(float) * FE_WIN);
+    for (int k1 = 0; k1 < 16; ++k1)
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const double ang = -2.0 * M_PI * (double)((n2 * k1) % 256) / 256.0;
+        t.w256t[k1 * 16 + n2] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+    for (int i = 0; i < FE_WIN; ++i) t.win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)FE_WIN));   // torch.hann_window(400)
+    cudaError_t e = cudaMemcpyToSymbol(g_fe, &t, sizeof(t));
     if (e != cudaSuccess) rc = (int)e;
   });
   return rc;
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 4-byte copy, zero-filled when !valid (src-size 0)
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -143,7 +159,10 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 
 constexpr int FE_ZLD = 17;                               // padded row of the 16x16 exchange buffer (float2 units)
 constexpr int FE_ZFRAME = 16 * FE_ZLD;                   // 272 float2 per frame (>= 257 floats for the magnitudes)
-constexpr int FE_SMEM_BYTES = FE_SAMPLES * 4 + FE_FRAMES * FE_ZFRAME * 8 + 256 * 8 + 1024;   // samples, exchange, W256 table
+constexpr int FE_OFF_Z = FE_SAMPLES * 4;                                   // 11648 (16-byte aligned)
+constexpr int FE_OFF_TAB = FE_OFF_Z + FE_FRAMES * FE_ZFRAME * 8;           // 46464
+constexpr int FE_SMEM_BYTES = FE_OFF_TAB + (int)sizeof(FeTables);          // 55.7 KB -> four CTAs per SM
+static_assert(FE_OFF_Z % 16 == 0 && FE_OFF_TAB % 16 == 0, "cp.async destinations must be 16-byte aligned");
 
 // 16 threads per frame, 16 frames per CTA.  The 512-point real FFT of a frame is a 256-point complex FFT of
 // z[n] = x[2n] + i x[2n+1], done as 16 x 16: thread n2 transforms z[16 n1 + n2] over n1 in registers, multiplies by
@@ -157,8 +176,8 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
                 float* __restrict__ freq_inds, float* __restrict__ mask, float* __restrict__ log_mel) {
   extern __shared__ __align__(16) uint8_t fe_smem[];
   float* s_x = reinterpret_cast<float*>(fe_smem);                                   // 2912 samples; later the log-mel tile
-  float2* s_z = reinterpret_cast<float2*>(fe_smem + FE_SAMPLES * 4);                // [16 frames][16][17]
-  float2* s_w256 = reinterpret_cast<float2*>(fe_smem + FE_SAMPLES * 4 + FE_FRAMES * FE_ZFRAME * 8);   // [k1][n2] = W256^{n2 k1}
+  float2* s_z = reinterpret_cast<float2*>(fe_smem + FE_OFF_Z);                      // [16 frames][16][17]
+  const FeTables& tab = *reinterpret_cast<const FeTables*>(fe_smem + FE_OFF_TAB);
   float (*s_out)[FE_MEL_LD] = reinterpret_cast<float (*)[FE_MEL_LD]>(s_x);          // [16][144] = 2304 floats <= 2912
 
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -202,16 +221,25 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     return;
   }
 
-  // ---- stage samples (zero tail pad, eval_caco_torch.py:72-78) and the W256 table (transposed: [k1][n2])
-  const float* wv = wave + (size_t)b * stride;
-  const int s0 = frame0 * FE_HOP;
-  for (int i = tid; i < FE_SAMPLES; i += 256) {
-    const int s = s0 + i;
-    s_x[i] = (s < n_samples) ? __ldg(wv + s) : 0.0f;
-  }
+  // ---- stage the tables and the samples (zero tail pad, eval_caco_torch.py:72-78) with cp.async: every copy of the CTA is
+  // in flight at once instead of one exposed global-load latency per loop trip
   {
-    const int k1 = tid >> 4, n2 = tid & 15;
-    s_w256[tid] = g_twiddle[(2 * n2 * k1) & 511];          // W256^m = W512^{2m}
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(&g_fe);
+    uint8_t* dst = fe_smem + FE_OFF_TAB;
+    for (int i = tid; i < (int)sizeof(FeTables) / 16; i += 256) cp_async16(dst + 16 * i, src + 16 * i);
+    const float* wv = wave + (size_t)b * stride;
+    const int s0 = frame0 * FE_HOP;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(wv + s0) & 15) == 0);
+    for (int i = tid; i < FE_SAMPLES / 4; i += 256) {
+      const int s = s0 + 4 * i;
+      if (aligned && s + 3 < n_samples) {
+        cp_async16(s_x + 4 * i, wv + s);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cp_async4_zfill(s_x + 4 * i + e, wv + (s + e < n_samples ? s + e : 0), s + e < n_samples);
+      }
+    }
+    cp_async_wait_all();
   }
   __syncthreads();
 
@@ -225,15 +253,15 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
       const int i0 = 2 * (16 * n1 + q), i1 = i0 + 1;
-      const float w0 = (i0 >= FE_WOFF && i0 < FE_WOFF + FE_WIN) ? __ldg(g_window + i0 - FE_WOFF) : 0.0f;
-      const float w1 = (i1 >= FE_WOFF && i1 < FE_WOFF + FE_WIN) ? __ldg(g_window + i1 - FE_WOFF) : 0.0f;
+      const float w0 = (i0 >= FE_WOFF && i0 < FE_WOFF + FE_WIN) ? tab.win[i0 - FE_WOFF] : 0.0f;
+      const float w1 = (i1 >= FE_WOFF && i1 < FE_WOFF + FE_WIN) ? tab.win[i1 - FE_WOFF] : 0.0f;
       const float2 xx = *reinterpret_cast<const float2*>(xf + i0);
       v[n1] = make_float2(xx.x * w0, xx.y * w1);
     }
   }
   dft16(v);                                                 // over n1 -> index k1
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], s_w256[k1 * 16 + q]);
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tab.w256t[k1 * 16 + q]);
 #pragma unroll
   for (int k1 = 0; k1 < 16; ++k1) zf[k1 * FE_ZLD + q] = v[k1];
   __syncwarp();
@@ -256,7 +284,7 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
     const float dr = zk.x - zc.x, di = zk.y + zc.y;
     const float orr = 0.5f * di, oi = -0.5f * dr;
-    const float2 w = g_twiddle[k];
+    const float2 w = tab.w512[k];
     const float xr = er + (w.x * orr - w.y * oi);
     const float xi = ei + (w.x * oi + w.y * orr);
     mag[k2] = sqrtf(xr * xr + xi * xi);
@@ -275,9 +303,10 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
 #pragma unroll
   for (int i = 0; i < FE_NMEL / 16; ++i) {
     const int m = q + 16 * i;
-    const int st = g_mel.start[m], cnt = g_mel.count[m];   // 9 KB table, L1/L2 resident
+    const int st = tab.mel_start[m], cnt = tab.mel_count[m];
+    const float* mw = tab.mel_w + tab.mel_woff[m];
     float acc = 0.0f;
-    for (int c = 0; c < cnt; ++c) acc = fmaf(s_mag[st + c], g_mel.w[m][c], acc);
+    for (int c = 0; c < cnt; ++c) acc = fmaf(s_mag[st + c], mw[c], acc);
     s_out[fr][m] = logf(acc + 1e-5f) * 0.2f + 0.9f;
   }
   __syncthreads();
