@@ -14,14 +14,15 @@ mask = torch.ones(B, S, device="cuda")
 mask[:, 496:] = 0
 lib = L.load()
 lib.caco_set_attention_impl(4)
-lib.caco_attn3_trace.argtypes = [C.c_void_p]
+trace_fn = lib.caco_attn3_trace
+trace_fn.argtypes = [C.c_void_p]
 for _ in range(2):
     ops.attention_audio(qkv, mask, H)
 buf = torch.zeros(2 * 64 * 8, dtype=torch.int64, device="cuda")
-lib.caco_attn3_trace(buf.data_ptr())
+trace_fn(buf.data_ptr())
 ops.attention_audio(qkv, mask, H)
 torch.cuda.synchronize()
-lib.caco_attn3_trace(None)
+trace_fn(None)
 t = buf.cpu().view(2, 64, 8)
 t0 = int(t[t > 0].min())
 names = [["iter", "inputs", "pA_seen", "pvA+qkA", "pB_seen", "pvB+qkB", "-", "-"],
