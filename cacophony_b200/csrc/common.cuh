@@ -21,7 +21,7 @@ int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
               int dim, cudaStream_t stream);
 int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
-                  int dim, cudaStream_t stream);
+                  int dim, int init, cudaStream_t stream);
 int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                     cudaStream_t stream);
 int attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,

@@ -224,8 +224,10 @@ static int audio_chunk(caco_model* m, const float* patches, const __half* patche
 
   // input projection + position embeddings (mae.py:133-142)
   if (patches16 == nullptr) CK(cast_f32_f16(patches, p16, (int64_t)R * P, st));
-  CK(gemm_f16(patches16 ? patches16 : p16, P, m->in_w, P, m->in_b, nullptr, 0, x, D, Ri, D, P, CACO_EPI_BIAS_F32, 0, 0, st));
-  CK(audio_add_pos(x, t_inds, f_inds, m->freq_emb, c.n_freq, Ri, D, st));
+  // x = pos(t) + freq_emb[f] written first (no read), then the projection accumulates onto it in place (L2 reductions):
+  // one pass over x less than project-then-add
+  CK(audio_add_pos(x, t_inds, f_inds, m->freq_emb, c.n_freq, Ri, D, 1, st));
+  CK(gemm_f16(patches16 ? patches16 : p16, P, m->in_w, P, m->in_b, x, D, x, D, Ri, D, P, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
   // pre-LN blocks (mae.py:80-99)
   for (int i = 0; i < c.audio_layers; ++i) {
     const caco_model::ALayer& l = m->al[i];

@@ -117,28 +117,49 @@ int layernorm(const float* x, const float* gamma, const float* beta, float eps, 
 // mae.py:102-109: angle = t * exp(2i * (-ln 1e4) / dim); x += cat[sin, cos];  mae.py:136-142: x += freq_emb[f]
 __global__ void __launch_bounds__(256)
 audio_add_pos_kernel(float* __restrict__ x, const float* __restrict__ time_inds, const float* __restrict__ freq_inds,
-                     const float* __restrict__ freq_emb, int n_freq, int rows, int dim) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+                     const float* __restrict__ freq_emb, int n_freq, int rows, int dim, int init) {
+  // one warp per APOS_ROWS consecutive rows: the frequencies w_i = exp(-2 i ln(1e4) / dim) of the lane's columns are
+  // computed once and reused.  init != 0: x = sincos + freq_emb (pure write: the input projection then accumulates onto it
+  // in place); init == 0: x += sincos + freq_emb.
+  constexpr int APOS_ROWS = 4, APOS_MAXI = 16;             // dim / 2 <= 32 * APOS_MAXI
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float t = time_inds[row];
-  int f = (int)freq_inds[row];   // .long() truncation
-  f = min(max(f, 0), n_freq - 1);
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * APOS_ROWS;
   const int half = dim / 2;
-  float* xr = x + (size_t)row * dim;
-  const float* fe = freq_emb + (size_t)f * dim;
-  for (int i = lane; i < half; i += 32) {
-    const float w = expf(((2.0f * (float)i) * -9.210340371976184f) / (float)dim);
-    float sn, cs;
-    sincosf(t * w, &sn, &cs);
-    xr[i] = (xr[i] + sn) + fe[i];
-    xr[i + half] = (xr[i + half] + cs) + fe[i + half];
+  float w[APOS_MAXI];
+#pragma unroll
+  for (int k = 0; k < APOS_MAXI; ++k) {
+    const int i = lane + 32 * k;
+    w[k] = expf(((2.0f * (float)i) * -9.210340371976184f) / (float)dim);
+  }
+  for (int r = 0; r < APOS_ROWS; ++r) {
+    const int row = row0 + r;
+    if (row >= rows) return;
+    const float t = time_inds[row];
+    int f = (int)freq_inds[row];   // .long() truncation
+    f = min(max(f, 0), n_freq - 1);
+    float* xr = x + (size_t)row * dim;
+    const float* fe = freq_emb + (size_t)f * dim;
+#pragma unroll
+    for (int k = 0; k < APOS_MAXI; ++k) {
+      const int i = lane + 32 * k;
+      if (i < half) {
+        float sn, cs;
+        sincosf(t * w[k], &sn, &cs);
+        if (init) {
+          xr[i] = sn + fe[i];
+          xr[i + half] = cs + fe[i + half];
+        } else {
+          xr[i] = (xr[i] + sn) + fe[i];
+          xr[i + half] = (xr[i + half] + cs) + fe[i + half];
+        }
+      }
+    }
   }
 }
 int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
-                  int dim, cudaStream_t stream) {
-  if (!x || !time_inds || !freq_inds || !freq_emb || rows <= 0 || dim <= 0 || (dim & 1)) return CACO_ERR_ARG;
-  audio_add_pos_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim);
+                  int dim, int init, cudaStream_t stream) {
+  if (!x || !time_inds || !freq_inds || !freq_emb || rows <= 0 || dim <= 0 || (dim & 1) || dim > 1024) return CACO_ERR_ARG;
+  audio_add_pos_kernel<<<(rows + 31) / 32, 256, 0, stream>>>(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim, init);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -195,35 +216,46 @@ int text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ K6 attention pool
-// One CTA (256 threads) per sample.  Phase 1: per token row (one warp each) optional LayerNorm, scores against the
-// folded queries u[h].  Phase 2: masked softmax per head.  Phase 3: weighted sum of the (normalised) rows.
+// One CTA (512 threads) per sample, ONE pass over the sample's rows (the two-pass form read every row twice from DRAM:
+// 787 MB per audio call, L2 hit rate 0.3 % — profiles/r01_notes.md).  Each warp walks its rows with an online softmax per
+// head: optional LayerNorm of the row, score against the folded query u[h], running maximum m, running sum l and a running
+// weighted row sum acc[h] held in registers (dim / 32 floats per lane and head), rescaled when the maximum grows.  The 16
+// warps' partial (m, l, acc) are merged through shared memory in a fixed order (deterministic).
 constexpr int POOL_MAX_HEADS = 4;
-constexpr int POOL_THREADS = 512, POOL_WARPS = POOL_THREADS / 32;   // 16 rows in flight per CTA in phase 1
+constexpr int POOL_THREADS = 512, POOL_WARPS = POOL_THREADS / 32;
+template <int HEADS>
 __global__ void __launch_bounds__(POOL_THREADS)
 attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, const float* __restrict__ u,
                  const float* __restrict__ cvec, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-                 float* __restrict__ hid_out, float* __restrict__ pooled, int S, int heads, int dim) {
+                 float* __restrict__ hid_out, float* __restrict__ pooled, int S, int dim) {
   extern __shared__ float sm[];
-  float* s_score = sm;                  // [heads][S]
-  float* s_mean = sm + heads * S;       // [S]
-  float* s_rstd = s_mean + S;           // [S]
-  __shared__ float s_red[POOL_MAX_HEADS][POOL_WARPS];
-  __shared__ float s_stat[POOL_MAX_HEADS][2];
+  float* s_part = sm;                                   // [warps][HEADS][dim]
+  __shared__ float s_m[POOL_WARPS][POOL_MAX_HEADS], s_l[POOL_WARPS][POOL_MAX_HEADS];
+  __shared__ float s_scale[POOL_WARPS][POOL_MAX_HEADS], s_inv[POOL_MAX_HEADS];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hb = hid + (size_t)b * S * dim;
   const float* mb = mask + (size_t)b * S;
   const int nv = dim / 128;
   const bool do_ln = ln_g != nullptr;
 
+  float m[HEADS], l[HEADS];
+  float4 acc[HEADS][ROW_MAX_V4];
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) {
+    m[h] = -INFINITY;
+    l[h] = 0.f;
+#pragma unroll
+    for (int c = 0; c < ROW_MAX_V4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int j = warp; j < S; j += POOL_WARPS) {
+    const bool live = mb[j] != 0.0f;
+    if (!live && !(do_ln && hid_out)) continue;          // a masked row only matters if its LayerNorm output was asked for
     float4 v[ROW_MAX_V4];
 #pragma unroll
     for (int c = 0; c < ROW_MAX_V4; ++c)
       if (c < nv) v[c] = *reinterpret_cast<const float4*>(hb + (size_t)j * dim + c * 128 + lane * 4);
-    RowStats st;
-    st.mean = 0.f; st.rstd = 1.f;
     if (do_ln) {
-      st = row_stats(v, nv, dim, eps);
+      const RowStats st = row_stats(v, nv, dim, eps);
 #pragma unroll
       for (int c = 0; c < ROW_MAX_V4; ++c)
         if (c < nv) {
@@ -237,7 +269,9 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
           if (hid_out) *reinterpret_cast<float4*>(hid_out + ((size_t)b * S + j) * dim + col) = v[c];
         }
     }
-    for (int h = 0; h < heads; ++h) {
+    if (!live) continue;
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) {
       float d = 0.f;
 #pragma unroll
       for (int c = 0; c < ROW_MAX_V4; ++c)
@@ -245,78 +279,82 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
           const float4 uu = *reinterpret_cast<const float4*>(u + (size_t)h * dim + c * 128 + lane * 4);
           d += (v[c].x * uu.x + v[c].y * uu.y) + (v[c].z * uu.z + v[c].w * uu.w);
         }
-      d = warp_sum(d);
-      if (lane == 0) s_score[h * S + j] = (mb[j] != 0.0f) ? d + cvec[h] : -INFINITY;
+      d = warp_sum(d) + cvec[h];
+      const float m_new = fmaxf(m[h], d);
+      const float keep = expf(m[h] - m_new);              // first live row: exp(-inf) = 0
+      const float p = expf(d - m_new);
+      l[h] = l[h] * keep + p;
+      m[h] = m_new;
+#pragma unroll
+      for (int c = 0; c < ROW_MAX_V4; ++c)
+        if (c < nv) {
+          acc[h][c].x = fmaf(p, v[c].x, acc[h][c].x * keep);
+          acc[h][c].y = fmaf(p, v[c].y, acc[h][c].y * keep);
+          acc[h][c].z = fmaf(p, v[c].z, acc[h][c].z * keep);
+          acc[h][c].w = fmaf(p, v[c].w, acc[h][c].w * keep);
+        }
     }
-    if (lane == 0) { s_mean[j] = st.mean; s_rstd[j] = st.rstd; }
+  }
+  // ---- merge the warps' partials
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) {
+    if (lane == 0) { s_m[warp][h] = m[h]; s_l[warp][h] = l[h]; }
+#pragma unroll
+    for (int c = 0; c < ROW_MAX_V4; ++c)
+      if (c < nv) *reinterpret_cast<float4*>(s_part + ((size_t)warp * HEADS + h) * dim + c * 128 + lane * 4) = acc[h][c];
   }
   __syncthreads();
-  // softmax per head (max, exp, sum) over S
-  for (int h = 0; h < heads; ++h) {
-    float mx = -INFINITY;
-    for (int j = tid; j < S; j += POOL_THREADS) mx = fmaxf(mx, s_score[h * S + j]);
-    mx = warp_max(mx);
-    if (lane == 0) s_red[h][warp] = mx;
-  }
-  __syncthreads();
-  if (tid < heads) {
-    float mx = -INFINITY;
-    for (int w = 0; w < POOL_WARPS; ++w) mx = fmaxf(mx, s_red[tid][w]);
-    s_stat[tid][0] = mx;
-  }
-  __syncthreads();
-  for (int h = 0; h < heads; ++h) {
-    const float mx = s_stat[h][0];
-    float sum = 0.f;
-    for (int j = tid; j < S; j += POOL_THREADS) {
-      const float e = expf(s_score[h * S + j] - mx);
-      s_score[h * S + j] = e;
-      sum += e;
+  if (tid < HEADS) {
+    float M = -INFINITY;
+    for (int w = 0; w < POOL_WARPS; ++w) M = fmaxf(M, s_m[w][tid]);
+    float L = 0.f;
+    for (int w = 0; w < POOL_WARPS; ++w) {
+      const float sc = (s_m[w][tid] == -INFINITY) ? 0.f : expf(s_m[w][tid] - M);     // a warp without live rows adds nothing
+      s_scale[w][tid] = sc;
+      L += s_l[w][tid] * sc;
     }
-    sum = warp_sum(sum);
-    if (lane == 0) s_red[h][warp] = sum;
+    s_inv[tid] = 1.0f / L;                                 // no live row at all: L = 0 -> NaN row, like torch.softmax
   }
   __syncthreads();
-  if (tid < heads) {
-    float sum = 0.f;
-    for (int w = 0; w < POOL_WARPS; ++w) sum += s_red[tid][w];
-    s_stat[tid][1] = 1.0f / sum;
-  }
-  __syncthreads();
-  // weighted sum: thread owns columns tid, tid+256, ...
   for (int col = tid; col < dim; col += POOL_THREADS) {
-    float acc[POOL_MAX_HEADS];
 #pragma unroll
-    for (int h = 0; h < POOL_MAX_HEADS; ++h) acc[h] = 0.f;
-    const float g = do_ln ? ln_g[col] : 1.f, bt = do_ln ? ln_b[col] : 0.f;
-#pragma unroll 8
-    for (int j = 0; j < S; ++j) {
-      float xv = hb[(size_t)j * dim + col];
-      if (do_ln) xv = (xv - s_mean[j]) * s_rstd[j] * g + bt;
-#pragma unroll
-      for (int h = 0; h < POOL_MAX_HEADS; ++h)
-        if (h < heads) acc[h] = fmaf(s_score[h * S + j], xv, acc[h]);
+    for (int h = 0; h < HEADS; ++h) {
+      float a = 0.f;
+      for (int w = 0; w < POOL_WARPS; ++w) a = fmaf(s_part[((size_t)w * HEADS + h) * dim + col], s_scale[w][h], a);
+      pooled[((size_t)b * HEADS + h) * dim + col] = a * s_inv[h];
     }
-    for (int h = 0; h < heads; ++h) pooled[((size_t)b * heads + h) * dim + col] = acc[h] * s_stat[h][1];
   }
 }
+
+template <int HEADS>
+static int launch_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
+                       const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int dim,
+                       cudaStream_t stream) {
+  const size_t smem = (size_t)POOL_WARPS * HEADS * dim * sizeof(float);
+  if (smem > 200 * 1024) return CACO_ERR_ARG;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_pool_kernel<HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e) return (int)e;
+    set = true;
+  }
+  attn_pool_kernel<HEADS><<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, dim);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 int attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
               const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads, int dim,
               cudaStream_t stream) {
   if (!hid || !mask || !u || !c || !pooled || batch <= 0 || seq <= 0 || heads <= 0 || heads > POOL_MAX_HEADS)
     return CACO_ERR_ARG;
   if ((dim % 128) || dim > 128 * ROW_MAX_V4) return CACO_ERR_ARG;
-  const size_t smem = (size_t)(heads + 2) * seq * sizeof(float);
-  if (smem > 200 * 1024) return CACO_ERR_ARG;
-  static size_t cur_max = 48 * 1024;
-  if (smem > cur_max) {
-    cudaError_t e = cudaFuncSetAttribute(attn_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e) return (int)e;
-    cur_max = smem;
+  switch (heads) {
+    case 1: return launch_pool<1>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
+    case 2: return launch_pool<2>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
+    case 3: return launch_pool<3>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
+    default: return launch_pool<4>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
   }
-  attn_pool_kernel<<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, heads, dim);
-  count_launch();
-  return (int)cudaGetLastError();
 }
 
 // fold a pooler's key projection into its (fixed) query: u[h,i] = sum_d qs[h,d] Wk[h*dh+d, i], c[h] = sum_d qs[h,d] bk[h*dh+d]
@@ -464,7 +502,7 @@ int caco_layernorm(const float* x, const float* gamma, const float* beta, float 
 }
 int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,
                        int dim, void* stream) {
-  return caco::audio_add_pos(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim, (cudaStream_t)stream);
+  return caco::audio_add_pos(x, time_inds, freq_inds, freq_emb, n_freq, rows, dim, 0, (cudaStream_t)stream);
 }
 int caco_text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
                        const float* type0, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
