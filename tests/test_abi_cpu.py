@@ -106,3 +106,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("no CPU", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links_without_python(tmp_path):
+    """include/caco_b200.h compiles as C99 and a plain-C program links libcaco_b200.so and gets answers from the
+    host-side entry points (tests/c/abi_smoke.c) — the drop-in boundary has no torch / C++ types in it."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not on PATH")
+    B.build()
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(L.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+           "-L" + libdir, "-lcaco_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi ok" in r.stdout, r.stdout + r.stderr
