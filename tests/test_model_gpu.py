@@ -119,3 +119,31 @@ def test_errors_mirror_reference_behaviour(synthetic_state_dict):
                                   torch.ones(1, 10).cuda())
     with pytest.raises(RuntimeError):
         cb.create_caco_model().get_text_embedding(torch.zeros(1, 4, dtype=torch.long), torch.ones(1, 4))
+
+
+def test_long_clip_30s_1500_tokens_matches_oracle(synthetic_state_dict):
+    """Maximum size the reference's loader produces for a 30 s clip (1500 patches = 3 k-blocks of the attention kernel's
+    512-key stride, 12 query tiles): embeddings within the 1e-3 bar of the CPU oracle."""
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    w = W.make_waveforms(31, 1, 480000, "noise")
+    e = model.encode_audio(torch.from_numpy(w).cuda(), max_patches=1500)
+    sd = synthetic_state_dict(c["seed"], c["sharp"])
+    ab = O.prepare_audio_batch(list(w), 1500)
+    assert int(ab["audio_mask"].sum()) == 1496
+    ref, _ = O.get_audio_embedding(sd, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"],
+                                   normalize=True)
+    assert rel_rows(e, ref) < REL_TOL
+
+
+def test_batch_larger_than_one_workspace_pass(synthetic_state_dict):
+    """More token rows than one pass handles (131 072): the engine chunks the batch; every clip's embedding must equal the
+    one it gets in a small batch (5 s clips keep the test short: 270 x 500 rows = 2 passes)."""
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    base = torch.from_numpy(W.make_waveforms(55, 6, 80000, "noise")).cuda()
+    w = base.repeat(45, 1)                                  # 270 clips, 6 distinct
+    e = model.encode_audio(w, max_patches=500)
+    e6 = model.encode_audio(base, max_patches=500)
+    assert e.shape == (270, 768) and torch.isfinite(e).all()
+    assert rel_rows(e[:6], e6) < 1e-6 and rel_rows(e[264:], e6) < 1e-6 and rel_rows(e[132:138], e6) < 1e-6
