@@ -286,7 +286,7 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
     const size_t o_x = carve(R * D * 4), o_x16 = carve(R * D * 2), o_a = carve(R * D * 4), o_a16 = carve(R * D * 2);
-    const size_t o_tmp = carve(R * D * 4), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2);
+    const size_t o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2);
     const size_t o_pool = carve((size_t)nb * D * 4), o_v = carve((size_t)nb * D * 4), o_e = carve((size_t)nb * D * 4);
     CK(ensure_ws(m, 1, off));
     uint8_t* w = (uint8_t*)m->ws[1];
@@ -294,7 +294,6 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
     __half* x16 = (__half*)(w + o_x16);
     float* a = (float*)(w + o_a);
     __half* a16 = (__half*)(w + o_a16);
-    float* tmp = (float*)(w + o_tmp);
     __half* qkv = (__half*)(w + o_qkv);
     __half* att = (__half*)(w + o_att);
     __half* mlp = (__half*)(w + o_mlp);
@@ -311,11 +310,12 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
       const caco_model::TLayer& l = m->tl[i];
       CK(gemm_f16(x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, D, CACO_EPI_BIAS_F16, 0, 0, st));
       CK(attention_text(qkv, mask_c, att, nb, T, c.text_heads, D / c.text_heads, st));
-      CK(gemm_f16(att, D, l.o_w, D, l.o_b, x, D, tmp, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
-      CK(layernorm(tmp, l.ln1_g, l.ln1_b, c.ln_eps, a, a16, Ri, D, st));
+      // the residual operand is dead after the add (post-LN), so the sum is accumulated in place (L2 reductions)
+      CK(gemm_f16(att, D, l.o_w, D, l.o_b, x, D, x, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(layernorm(x, l.ln1_g, l.ln1_b, c.ln_eps, a, a16, Ri, D, st));
       CK(gemm_f16(a16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, D, CACO_EPI_BIAS_GELU_F16, 0, 0, st));
-      CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, a, D, tmp, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
-      CK(layernorm(tmp, l.ln2_g, l.ln2_b, c.ln_eps, x, x16, Ri, D, st));
+      CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, a, D, a, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(layernorm(a, l.ln2_g, l.ln2_b, c.ln_eps, x, x16, Ri, D, st));
     }
     if (hidden_out) {
       cudaError_t e = cudaMemcpyAsync(hidden_out + (size_t)b0 * T * D, x, R * D * 4, cudaMemcpyDeviceToDevice, st);

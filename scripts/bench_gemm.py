@@ -18,6 +18,7 @@ SHAPES = [  # (name, M, N, K, epi)
     ("fc2", 128000, 768, 3072, L.EPI_BIAS_RESID_F32),
     ("in", 128000, 768, 256, L.EPI_BIAS_F32),
     ("t_qkv", 8192, 2304, 768, L.EPI_BIAS_F16),
+    ("t_out", 8192, 768, 768, L.EPI_BIAS_RESID_F32),
     ("t_fc1", 8192, 3072, 768, L.EPI_BIAS_GELU_F16),
     ("t_fc2", 8192, 768, 3072, L.EPI_BIAS_RESID_F32),
 ]
