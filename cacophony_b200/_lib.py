@@ -39,6 +39,7 @@ SIGNATURES = {
     "caco_gemm_f16": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "caco_set_gemm_variant": (None, [_I]),
     "caco_set_gemm_resid_red": (None, [_I]),
+    "caco_set_pdl": (None, [_I]),
     "caco_gemm_profile": (None, [_I]),
     "caco_gemm_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "caco_cast_f32_f16": (_I, [_P, _P, _L, _P]),

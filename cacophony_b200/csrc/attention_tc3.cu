@@ -96,6 +96,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + B_TMEMSLOT);
+  pdl_wait();      // the QKV projection must have completed before any q/k/v tile is fetched
+  pdl_launch();
 
   auto decode = [&](int it, int& b, int& h, int& q0) {
     const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -437,7 +439,8 @@ int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch
   }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;
-  attention_tc3_kernel<<<grid, 384, smem, stream>>>(m64, m32, o64, o32, a);
+  cudaError_t le = launch_pdl(attention_tc3_kernel, dim3(grid), dim3(384), smem, stream, m64, m32, o64, o32, a);
+  if (le != cudaSuccess) return (int)le;
   count_launch();
   return (int)cudaGetLastError();
 }

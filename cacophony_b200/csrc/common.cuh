@@ -12,6 +12,23 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int num_sms();
 
+// programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch) for the tower kernels; 0 = ordinary stream order
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // op-level entry points implemented across the .cu files (C++ side of the C ABI)
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
              int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream);

@@ -140,6 +140,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; operands and outputs are touched only below
+  pdl_launch();
 
   const int num_tiles = g.num_m_blocks * g.num_n_blocks;
   const int first_tile = blockIdx.x / CG;
@@ -365,6 +367,7 @@ int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
 }
 
+int g_pdl = 1;
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -396,13 +399,15 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
   count_launch();
   return (int)e;
@@ -504,6 +509,7 @@ extern "C" int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, con
 
 extern "C" void caco_set_gemm_variant(int variant) { caco::g_gemm_variant = variant; }
 extern "C" void caco_set_gemm_resid_red(int enable) { caco::g_resid_red = enable; }
+extern "C" void caco_set_pdl(int enable) { caco::g_pdl = enable; }
 
 extern "C" void caco_gemm_profile(int enable) {
   caco::g_prof.on = enable != 0;

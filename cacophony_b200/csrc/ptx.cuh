@@ -305,6 +305,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_ma
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (prologue: barrier init, tensor-memory
+// allocation, descriptor prefetch) while its predecessor in the stream is still draining; pdl_wait() blocks until the
+// predecessor has completed and its writes are visible, pdl_launch() lets the successor start its own prologue.  Both are
+// no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2, 2^-22 relative error, exp2(-inf) = 0
   float y;

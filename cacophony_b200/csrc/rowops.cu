@@ -80,6 +80,8 @@ __device__ __forceinline__ void store_row(const float4& y, float* o32, __half* o
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  float* __restrict__ o32, __half* __restrict__ o16, int rows, int dim) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -108,7 +110,8 @@ int layernorm(const float* x, const float* gamma, const float* beta, float eps, 
               int dim, cudaStream_t stream) {
   if (!x || !gamma || !beta || rows <= 0 || dim <= 0 || (dim % 128) || dim > 128 * ROW_MAX_V4) return CACO_ERR_ARG;
   if (!out_f32 && !out_f16) return CACO_ERR_ARG;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out_f32, (__half*)out_f16, rows, dim);
+  cudaError_t le = launch_pdl(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, gamma, beta, eps, out_f32, (__half*)out_f16, rows, dim);
+  if (le != cudaSuccess) return (int)le;
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -67,6 +67,10 @@ void caco_set_gemm_variant(int variant);
 /* CACO_EPI_BIAS_RESID_F32 with resid == out (in-place residual update): 1 (default) = the add is done by the L2 with
  * red.global.add.v4.f32, 0 = load/add/store in the SM.  Same fp32 result; a measurement switch. */
 void caco_set_gemm_resid_red(int enable);
+/* Programmatic dependent launch of the tower kernels (GEMM, LayerNorm, audio attention): 1 (default) = a kernel's prologue
+ * (barrier init, tensor-memory allocation) overlaps its predecessor's tail and it waits with griddepcontrol.wait before
+ * touching data; 0 = ordinary stream order.  Same results; a measurement switch. */
+void caco_set_pdl(int enable);
 /* live profiling for bench.py: CUDA events around every GEMM launch on its stream.  caco_gemm_profile(1) resets and
  * starts recording; caco_gemm_profile_read synchronises the device and returns the launch count, summed device
  * time (ms) and summed algorithmic FLOPs (2*M*N*K). */

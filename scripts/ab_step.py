@@ -14,7 +14,9 @@ from cacophony_b200 import _lib as L
 lib = L.load()
 torch.manual_seed(0)
 model = cb.create_caco_model().cuda()
-wave, ids, mask = [t.cuda() for t in bench.synth_inputs(256, 0)]
+import os
+BATCH = int(os.environ.get("AB_BATCH", "256"))
+wave, ids, mask = [t.cuda() for t in bench.synth_inputs(BATCH, 0)]
 arms = []
 for a in sys.argv[1:]:
     name, spec = a.split("=")

@@ -1,5 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 3 --no-cpu --profile --serial-towers > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
-python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt
+AB_BATCH=1 timeout 600 python scripts/ab_step.py pdl=caco_set_pdl:1 nopdl=caco_set_pdl:0 2>&1 | tail -1
+AB_BATCH=8 timeout 600 python scripts/ab_step.py pdl=caco_set_pdl:1 nopdl=caco_set_pdl:0 2>&1 | tail -1
