@@ -1,3 +1,3 @@
 #!/bin/bash
-AB_BATCH=1 timeout 600 python scripts/ab_step.py pdl=caco_set_pdl:1 nopdl=caco_set_pdl:0 2>&1 | tail -1
-AB_BATCH=8 timeout 600 python scripts/ab_step.py pdl=caco_set_pdl:1 nopdl=caco_set_pdl:0 2>&1 | tail -1
+mkdir -p gpurun_out
+timeout 600 python scripts/bench_latency.py > gpurun_out/bench_latency.jsonl 2> gpurun_out/bench_latency.err; echo "rc=$?"; cat gpurun_out/bench_latency.jsonl; tail -5 gpurun_out/bench_latency.err

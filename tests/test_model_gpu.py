@@ -147,3 +147,22 @@ def test_batch_larger_than_one_workspace_pass(synthetic_state_dict):
     e6 = model.encode_audio(base, max_patches=500)
     assert e.shape == (270, 768) and torch.isfinite(e).all()
     assert rel_rows(e[:6], e6) < 1e-6 and rel_rows(e[264:], e6) < 1e-6 and rel_rows(e[132:138], e6) < 1e-6
+
+
+def test_graph_replay_is_bit_equal_to_eager(synthetic_state_dict):
+    """serving.GraphedPairs: the whole step captured into one CUDA graph (text tower on its side stream, PDL edges) gives
+    exactly the eager result, also after the static input buffers are refilled with a second request."""
+    from cacophony_b200.serving import GraphedPairs
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    g = GraphedPairs(model, 3, 80000, 16, max_patches=500)
+    for seed in (5, 6):
+        w = torch.from_numpy(W.make_waveforms(seed, 3, 80000, "noise")).cuda()
+        ids, mask = W.make_captions(seed, 3, 16, lens=[16, 5, 9])
+        ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda().float()
+        at, ta = g(w, ids, mask)
+        a, t = model.encode_pairs(w, ids, mask, max_patches=500)
+        r_at, r_ta = model.similarity(a, t)
+        assert torch.equal(at, r_at) and torch.equal(ta, r_ta)
+    with pytest.raises(ValueError):
+        g(w[:2], ids[:2], mask[:2])
