@@ -320,6 +320,29 @@ def run_ours(args):
             "timed_on": f"serial-stream replay of the same {args.steps} steps ({ms_serial / args.steps:.2f} ms/step), right after the main region",
             "whole_step_frac": round(value / world * GFLOP_PER_PAIR / 1e3 / peaks["bf16_sustained"], 4)}
 
+    # ---- HBM-bound side of the metric ("encoder HBM GB/s vs peak"): the LayerNorm kernel at the tower's shape, timed alone
+    from cacophony_b200 import ops as cops
+    xr = torch.randn(B * MAX_PATCHES, 768, device=dev)
+    gam = torch.ones(768, device=dev)
+    for _ in range(3):
+        cops.layernorm(xr, gam, gam, want_f32=False, want_f16=True)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    h0.record()
+    for _ in range(20):
+        cops.layernorm(xr, gam, gam, want_f32=False, want_f16=True)
+    h1.record()
+    torch.cuda.synchronize()
+    ln_ms = h0.elapsed_time(h1) / 20
+    ln_bytes = xr.numel() * 6                                # 4 B read + 2 B written per element
+    ln_gbs = ln_bytes / (ln_ms / 1e3) / 1e9
+    roof_hbm = {"bound": "hbm", "kernel": "layernorm_kernel (fp32 in, fp16 out; 24 launches per clip batch in the audio tower)",
+                "achieved": round(ln_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ln_gbs / peaks["hbm"], 4),
+                "bytes_per_launch": ln_bytes, "us_per_launch": round(ln_ms * 1e3, 2),
+                "timed_on": "20 back-to-back launches on a 393 MB input (> L2), CUDA events",
+                "traffic_note": "ncu: 0.393 GB read + 0.168 GB written per launch (profiles/r01_ncu_full_summary.csv)"}
+    del xr
+
     cpu = None
     if sd_cpu is not None:
         v, dt, n_pass = cpu_pairs_per_s(sd_cpu, 16, 2, 1, budget_s=12.0)
@@ -338,7 +361,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(ms_e2e / args.steps, 3), "checksum": checksum},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

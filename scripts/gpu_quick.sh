@@ -1,23 +1,6 @@
 #!/bin/bash
-python - <<'PY'
-import sys, json, torch
-sys.path.insert(0, ".")
-from cacophony_b200 import _lib as L, ops
-B,S,H,dh=256,500,8,96
-qkv=(torch.randn(B,S,3*H*dh,device="cuda")).half(); mask=torch.ones(B,S,device="cuda"); mask[:,496:]=0
-lib=L.load(); lib.caco_set_attention_impl(4)
-def t():
-    for _ in range(3): ops.attention_audio(qkv,mask,H)
-    torch.cuda.synchronize()
-    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20): ops.attention_audio(qkv,mask,H)
-    e1.record(); torch.cuda.synchronize()
-    return round(e0.elapsed_time(e1)/20,4)
-res={"spec":[], "two_pass":[], "old":[]}
-for r in range(4):
-    lib.caco_attn3_set_speculative(1); res["spec"].append(t())
-    lib.caco_attn3_set_speculative(0); res["two_pass"].append(t())
-    lib.caco_set_attention_impl(6); res["old"].append(t()); lib.caco_set_attention_impl(4)
-print(json.dumps(res))
-PY
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,power.limit,temperature.gpu,clocks.max.sm --format=csv
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['ms_per_step'], d['clocks'], d['roofline']['achieved'], d['roofline_hbm']['achieved'])"
+timeout 600 python scripts/ab_step.py pdl=caco_set_pdl:1 nopdl=caco_set_pdl:0 2>&1 | tail -1
