@@ -211,3 +211,15 @@ def test_hear_embeddings(model):
     e_ref, hid = model.get_audio_embedding(**ab, normalize=True)
     assert rel_rows(scene[None], e_ref) < 2e-6
     np.testing.assert_allclose(ev_emb, E.avg_pool_tokens(hid.cpu().numpy(), 8)[0], rtol=1e-5, atol=1e-5)
+
+
+def test_text_padding_trim_is_exact(model):
+    """Prompts padded to T = 100 (config 5): running the tower on the first 16 columns gives the same embeddings."""
+    ids, mask = W.make_captions(21, 9, 100, lens=[8, 9, 10, 11, 12, 8, 12, 3, 2])
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    full = ev.embed_text_ids(model, ids, mask, trim_padding=False)
+    trim = ev.embed_text_ids(model, ids, mask, trim_padding=True)
+    assert rel_rows(trim, full) < 2e-6
+    holes = mask.clone()
+    holes[0, 3] = 0                                       # a hole in a mask must not move the trim point
+    assert rel_rows(ev.embed_text_ids(model, ids, holes), ev.embed_text_ids(model, ids, holes, trim_padding=False)) < 2e-6
