@@ -166,3 +166,34 @@ def test_graph_replay_is_bit_equal_to_eager(synthetic_state_dict):
         assert torch.equal(at, r_at) and torch.equal(ta, r_ta)
     with pytest.raises(ValueError):
         g(w[:2], ids[:2], mask[:2])
+
+
+def test_full_bench_size_properties(synthetic_state_dict):
+    """BASELINE config 3 at full size (256 pairs, 10 s clips, 32-token captions), where the CPU oracle would take minutes:
+    size-independent properties instead — run-to-run bit-determinism, batch invariance of single rows, ta == atᵀ, unit norms,
+    |logit| <= exp(logit_scale), and a handful of rows against the oracle."""
+    import math
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    B = 256
+    w = torch.from_numpy(W.make_waveforms(200, B, 160000, "noise")).cuda()
+    ids, mask = W.make_captions(200, B, 32, lens=[32, 20, 9, 4, 17])
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    a1, t1 = model.encode_pairs(w, ids, mask, max_patches=500)
+    at1, ta1 = model.similarity(a1, t1)
+    a2, t2 = model.encode_pairs(w, ids, mask, max_patches=500)
+    assert torch.equal(a1, a2) and torch.equal(t1, t2)                        # deterministic (no atomics with >1 writer)
+    assert at1.shape == (B, B) and torch.equal(ta1, at1.t().contiguous())
+    np.testing.assert_allclose(a1.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)
+    np.testing.assert_allclose(t1.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)
+    assert float(at1.abs().max()) <= math.exp(W.LOGIT_SCALE_INIT) * (1 + 1e-5)
+    rows = [0, 101, 255]
+    a_alone = model.encode_audio(w[rows], max_patches=500)
+    t_alone = model.encode_text(ids[rows], mask[rows])
+    assert rel_rows(a1[rows], a_alone) < 1e-6 and rel_rows(t1[rows], t_alone) < 1e-6
+    sd = synthetic_state_dict(c["seed"], c["sharp"])
+    ab = O.prepare_audio_batch([w[101].cpu().numpy()], 500)
+    a_ref, _ = O.get_audio_embedding(sd, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"],
+                                     normalize=True)
+    t_ref, _ = O.get_text_embedding(sd, ids[[101]].cpu(), mask[[101]].cpu(), normalize=True)
+    assert rel_rows(a1[[101]], a_ref) < REL_TOL and rel_rows(t1[[101]], t_ref) < REL_TOL
