@@ -1,4 +1,6 @@
 #!/bin/bash
+# quick GPU round: the GPU test suite, smoke(), one bench line
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitizer_smoke.log 2>&1; echo "memcheck smoke rc=$?"; tail -6 gpurun_out/sanitizer_smoke.log
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_eval_gpu.py -x -q -k "topk or retrieval_metric or avg_pool or ragged_frontend or resample" > gpurun_out/sanitizer_eval.log 2>&1; echo "memcheck eval rc=$?"; tail -6 gpurun_out/sanitizer_eval.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
