@@ -223,3 +223,17 @@ def test_text_padding_trim_is_exact(model):
     holes = mask.clone()
     holes[0, 3] = 0                                       # a hole in a mask must not move the trim point
     assert rel_rows(ev.embed_text_ids(model, ids, holes), ev.embed_text_ids(model, ids, holes, trim_padding=False)) < 2e-6
+
+
+def test_load_audio_wav_file_matches_reference_pipeline(tmp_path):
+    """eval_utils.py:6-16 end to end for a 44.1 kHz stereo int16 WAV: read, channel mean, Fourier resample to 16 kHz."""
+    from scipy.io import wavfile
+    rng = np.random.default_rng(4)
+    pcm = (rng.standard_normal((22050, 2)) * 3000).astype(np.int16)
+    path = str(tmp_path / "clip.wav")
+    wavfile.write(path, 44100, pcm)
+    got = loader.load_audio(path, 44100, "cuda").cpu().numpy()
+    ref = (pcm.astype(np.float32) / 32768.0).mean(axis=-1)              # what soundfile.read returns for int16 PCM, then :9-10
+    ref = E.resample(ref.astype(np.float64), 44100)
+    assert got.shape == ref.shape == (8000,)
+    assert np.abs(got - ref).max() < 5e-6
