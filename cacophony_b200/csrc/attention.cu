@@ -264,12 +264,12 @@ int attention_audio(const void* qkv, const float* mask, void* out, int batch, in
   dim3 grid((seq + AT_BM - 1) / AT_BM, heads, batch);
   cudaError_t e;
   if (dh == 96) {
-    static bool set96 = false;
-    if (!set96) { e = cudaFuncSetAttribute(attention_audio_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::SMEM_BYTES); if (e) return (int)e; set96 = true; }
+    static PerDeviceOnce set96;
+    if (set96.first()) { e = cudaFuncSetAttribute(attention_audio_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::SMEM_BYTES); if (e) return (int)e; set96.done(); }
     attention_audio_kernel<96><<<grid, 128, AttnCfg<96>::SMEM_BYTES, stream>>>((const __half*)qkv, mask, (__half*)out, seq, heads, scale_log2);
   } else if (dh == 64) {
-    static bool set64 = false;
-    if (!set64) { e = cudaFuncSetAttribute(attention_audio_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES); if (e) return (int)e; set64 = true; }
+    static PerDeviceOnce set64;
+    if (set64.first()) { e = cudaFuncSetAttribute(attention_audio_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES); if (e) return (int)e; set64.done(); }
     attention_audio_kernel<64><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>((const __half*)qkv, mask, (__half*)out, seq, heads, scale_log2);
   } else {
     return CACO_ERR_ARG;
@@ -286,11 +286,11 @@ int attention_text(const void* qkv, const float* key_mask, void* out, int batch,
   if (!qkv || !key_mask || !out || batch <= 0 || T <= 0 || heads <= 0 || dh != 64) return CACO_ERR_ARG;
   // the flash-style warp-MMA kernel with the causal predicate: one CTA per (64 query rows, head, caption).  The scalar
   // per-(caption, head) kernel above took 0.10 ms per layer at B = 256, T = 32 (latency-bound shuffle chains).
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(attention_audio_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES);
     if (e) return (int)e;
-    attr = true;
+    attr.done();
   }
   dim3 grid((T + AT_BM - 1) / AT_BM, heads, batch);
   attention_audio_kernel<64, true><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>(

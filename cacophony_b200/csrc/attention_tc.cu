@@ -310,11 +310,11 @@ int attention_audio_tc(const void* qkv, const float* mask, void* out, int batch,
   if ((rc = make_map3(&mq1, qkv, batch, seq, ld, 32, TA_BM, false))) return rc;
   if ((rc = make_map3(&mkv0, qkv, batch, seq, ld, 64, TA_BN, true))) return rc;
   if ((rc = make_map3(&mk1, qkv, batch, seq, ld, 32, TA_BN, false))) return rc;
-  static size_t cur = 0;
-  if (smem > cur) {
+  static PerDeviceMax smem_max;
+  if (smem_max.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return (int)e;
-    cur = smem;
+    smem_max.set(smem);
   }
   dim3 grid((seq + TA_BM - 1) / TA_BM, heads, batch);
   attention_tc_kernel<<<grid, 192, smem, stream>>>(mq0, mq1, mkv0, mk1, mask, (__half*)out, seq, heads,

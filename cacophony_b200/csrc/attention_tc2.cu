@@ -417,11 +417,11 @@ int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch
   if ((rc = make_map3b(&mq1, qkv, batch, seq, ld, 32, BM, false))) return rc;
   if ((rc = make_map3b(&mkv0, qkv, batch, seq, ld, 64, BN, true))) return rc;
   if ((rc = make_map3b(&mk1, qkv, batch, seq, ld, 32, BN, false))) return rc;
-  static size_t cur = 0;
-  if (smem > cur) {
+  static PerDeviceMax smem_max;
+  if (smem_max.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return (int)e;
-    cur = smem;
+    smem_max.set(smem);
   }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;

@@ -431,11 +431,11 @@ int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch
   if ((rc = make_map3c(&m32, qkv, batch, seq, ld, 32, BM, false))) return rc;
   if ((rc = make_map3c(&o64, out, batch, seq, heads * dh, 64, 32, true))) return rc;      // per-warp store boxes: 32 rows
   if ((rc = make_map3c(&o32, out, batch, seq, heads * dh, 32, 32, false))) return rc;
-  static size_t cur = 0;
-  if (smem > cur) {
+  static PerDeviceMax smem_max;
+  if (smem_max.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return (int)e;
-    cur = smem;
+    smem_max.set(smem);
   }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;

@@ -12,6 +12,27 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int num_sms();
 
+// Function attributes (max dynamic shared memory) and __device__ tables are per DEVICE: one-time work is tracked per
+// device, so a process that drives several GPUs (model.to("cuda:1") next to "cuda:0") initialises each of them.
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool first() {                       // true exactly once per device (benign if two threads race: the work is idempotent)
+    const uint64_t bit = 1ull << current_device();
+    return !(mask.load(std::memory_order_acquire) & bit);
+  }
+  void done() { mask.fetch_or(1ull << current_device(), std::memory_order_release); }
+};
+struct PerDeviceMax {                  // largest value already configured on each device (for growing smem opt-ins)
+  size_t cur[64] = {};
+  bool need(size_t v) const { return v > cur[current_device()]; }
+  void set(size_t v) { cur[current_device()] = v; }
+};
+
 // programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch) for the tower kernels; 0 = ordinary stream order
 extern int g_pdl;
 template <typename... KArgs, typename... Args>

@@ -70,13 +70,14 @@ void mel_filterbank_host(float* out) {
 }
 
 static int frontend_init() {
-  static int rc = -100;
+  // host tables once per process, the __device__ copy once per device
+  static FeTables t;
+  static int host_rc = -100;
   static std::once_flag once;
   std::call_once(once, [] {
     std::vector<float> fb(FE_NFREQ * FE_NMEL);
     mel_filterbank_host(fb.data());
-    static FeTables t;
-    rc = 0;
+    host_rc = 0;
     int woff = 0;
     for (int m = 0; m < FE_NMEL; ++m) {
       int lo = -1, hi = -1;
@@ -85,7 +86,7 @@ static int frontend_init() {
       t.mel_start[m] = lo < 0 ? 0 : lo;
       t.mel_count[m] = lo < 0 ? 0 : hi - lo + 1;
       t.mel_woff[m] = woff;
-      if (t.mel_count[m] > FE_MAXW || woff + t.mel_count[m] > 512) { rc = CACO_ERR_STATE; return; }
+      if (t.mel_count[m] > FE_MAXW || woff + t.mel_count[m] > 512) { host_rc = CACO_ERR_STATE; return; }
       for (int j = 0; j < t.mel_count[m]; ++j) t.mel_w[woff++] = fb[(t.mel_start[m] + j) * FE_NMEL + m];
     }
     for (; woff < 512; ++woff) t.mel_w[woff] = 0.0f;
@@ -99,10 +100,15 @@ static int frontend_init() {
         t.w256t[k1 * 16 + n2] = make_float2((float)cos(ang), (float)sin(ang));
       }
     for (int i = 0; i < FE_WIN; ++i) t.win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)FE_WIN));   // torch.hann_window(400)
-    cudaError_t e = cudaMemcpyToSymbol(g_fe, &t, sizeof(t));
-    if (e != cudaSuccess) rc = (int)e;
   });
-  return rc;
+  if (host_rc) return host_rc;
+  static PerDeviceOnce uploaded;
+  if (uploaded.first()) {
+    cudaError_t e = cudaMemcpyToSymbol(g_fe, &t, sizeof(t));
+    if (e != cudaSuccess) return (int)e;
+    uploaded.done();
+  }
+  return 0;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -353,11 +359,11 @@ int frontend(const float* wave, const int* lengths, int batch, int n_samples, in
   int gx = T_out;
   if (log_mel != nullptr) gx = max(gx, (n_frames + FE_FRAMES - 1) / FE_FRAMES);
   dim3 grid(gx, batch);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_once.done();
   }
   frontend_kernel<<<grid, 256, FE_SMEM_BYTES, stream>>>(wave, lengths, n_samples, n_samples, max_patches, patches,
                                             reinterpret_cast<__half*>(patches_f16), time_inds, freq_inds, mask, log_mel);

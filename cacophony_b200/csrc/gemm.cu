@@ -382,11 +382,11 @@ template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<CG, BN, STAGES, EPI_WARPS>;
   auto kern = gemm_f16_kernel<CG, BN, STAGES, EPI_WARPS, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_once.done();
   }
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   int ctas = num_sms();

@@ -335,11 +335,11 @@ static int launch_pool(const float* hid, const float* mask, const float* u, cons
                        cudaStream_t stream) {
   const size_t smem = (size_t)POOL_WARPS * HEADS * dim * sizeof(float);
   if (smem > 200 * 1024) return CACO_ERR_ARG;
-  static bool set = false;
-  if (!set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_pool_kernel<HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e) return (int)e;
-    set = true;
+    attr_once.done();
   }
   attn_pool_kernel<HEADS><<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, dim);
   count_launch();

@@ -197,3 +197,24 @@ def test_full_bench_size_properties(synthetic_state_dict):
                                      normalize=True)
     t_ref, _ = O.get_text_embedding(sd, ids[[101]].cpu(), mask[[101]].cpu(), normalize=True)
     assert rel_rows(a1[[101]], a_ref) < REL_TOL and rel_rows(t1[[101]], t_ref) < REL_TOL
+
+
+def test_second_device_in_the_same_process(synthetic_state_dict):
+    """Function attributes and __device__ tables are per device: a model on cuda:1 must work after cuda:0 was used
+    (skipped on single-GPU boxes; the supported deployment is still one process per GPU)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    c = MODEL_CASES["model_s0"]
+    m0 = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    w = torch.from_numpy(W.make_waveforms(9, 2, 80000, "noise"))
+    ids, mask = W.make_captions(9, 2, 32, lens=[32, 11])
+    ids, mask = torch.from_numpy(ids), torch.from_numpy(mask)
+    a0, t0 = m0.encode_pairs(w.cuda(0), ids.cuda(0), mask.cuda(0), max_patches=500)
+    m1 = cb.create_caco_model()
+    m1.load_state_dict(synthetic_state_dict(c["seed"], c["sharp"]))
+    m1 = m1.to("cuda:1")
+    a1, t1 = m1.encode_pairs(w.cuda(1), ids.cuda(1), mask.cuda(1), max_patches=500)
+    at1, _ = m1.similarity(a1, t1)
+    torch.cuda.synchronize(1)
+    assert torch.equal(a0.cpu(), a1.cpu()) and torch.equal(t0.cpu(), t1.cpu())
+    assert at1.device.index == 1 and torch.isfinite(at1).all()
