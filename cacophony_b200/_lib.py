@@ -25,7 +25,8 @@ _ERR = {-1: "CACO_ERR_ARG (bad shape / null pointer / unsupported size)",
 class CacoConfig(C.Structure):
     _fields_ = [("hidden", C.c_int), ("ffn", C.c_int), ("patch_dim", C.c_int), ("audio_layers", C.c_int),
                 ("audio_heads", C.c_int), ("n_freq", C.c_int), ("pool_heads", C.c_int), ("text_layers", C.c_int),
-                ("text_heads", C.c_int), ("vocab", C.c_int), ("max_pos", C.c_int), ("ln_eps", C.c_float)]
+                ("text_heads", C.c_int), ("vocab", C.c_int), ("max_pos", C.c_int), ("ln_eps", C.c_float),
+                ("audio_ln_eps", C.c_float)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -37,16 +38,16 @@ SIGNATURES = {
     "caco_frontend": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "caco_frontend_ragged": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "caco_gemm_f16": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "caco_set_gemm_variant": (None, [_I]),
-    "caco_set_gemm_resid_red": (None, [_I]),
-    "caco_set_pdl": (None, [_I]),
+    "caco_gemm_f16_wsplit": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "caco_cast_f32_f16_split": (_I, [_P, _P, _L, _L, _P]),
+    "caco_set_default_option": (_I, [C.c_char_p, _I]),
+    "caco_saturation_count": (C.c_uint, [_I]),
     "caco_gemm_profile": (None, [_I]),
     "caco_gemm_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "caco_cast_f32_f16": (_I, [_P, _P, _L, _P]),
     "caco_layernorm": (_I, [_P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "caco_audio_add_pos": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "caco_attention_audio": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
-    "caco_set_attention_impl": (None, [_I]),
     "caco_attention_text": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "caco_text_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
     "caco_attn_pool": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _P]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "caco_model_destroy": (None, [_P]),
     "caco_model_set_tensor": (_I, [_P, C.c_char_p, _P, _L]),
     "caco_model_pack": (_I, [_P, _P]),
+    "caco_model_set_option": (_I, [_P, C.c_char_p, _I]),
+    "caco_model_generation": (C.c_uint64, [_P]),
     "caco_model_audio_embedding": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_text_embedding": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_encode_audio": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

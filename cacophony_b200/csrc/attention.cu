@@ -242,23 +242,16 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
   }
 }
 
-int attention_audio_tc(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
-                       cudaStream_t stream);
-int attention_audio_tc2(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
-                        cudaStream_t stream);
 int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                         cudaStream_t stream);
-static int g_attn_impl = 0;   // 0 = auto, 1 = warp-level mma.sync kernel, 2 = tcgen05 one-tile kernel, 3 = tcgen05 persistent kernel
 
 int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                     cudaStream_t stream) {
   if (!qkv || !mask || !out || batch <= 0 || seq <= 0 || heads <= 0) return CACO_ERR_ARG;
-  if (dh == 96 && (g_attn_impl == 0 || g_attn_impl == 4) && seq <= 2304)
-    return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
-  if (dh == 96 && g_attn_impl != 1) {
-    if (g_attn_impl != 2 && seq <= 1856) return attention_audio_tc2(qkv, mask, out, batch, seq, heads, dh, stream);
-    if (seq <= 1728) return attention_audio_tc(qkv, mask, out, batch, seq, heads, dh, stream);
-  }
+  // head_dim 96 (the checkpoint's audio tower): the persistent ping-pong tcgen05 kernel, up to 4096 keys (its per-item key
+  // bias lives in shared memory); anything else (head_dim 64 configurations, longer sequences) takes the warp-level
+  // flash kernel below.
+  if (dh == 96 && seq <= 4096) return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
   if ((heads * dh) % 8) return CACO_ERR_ARG;
   const float scale_log2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   dim3 grid((seq + AT_BM - 1) / AT_BM, heads, batch);
@@ -301,7 +294,6 @@ int attention_text(const void* qkv, const float* key_mask, void* out, int batch,
 
 }  // namespace caco
 
-extern "C" void caco_set_attention_impl(int impl) { caco::g_attn_impl = impl; }
 extern "C" int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                                     void* stream) {
   return caco::attention_audio(qkv, mask, out, batch, seq, heads, dh, (cudaStream_t)stream);

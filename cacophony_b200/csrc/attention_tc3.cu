@@ -58,6 +58,52 @@ struct Attn3Args {
   float scale_log2;
 };
 
+// 2^x on the FMA/ALU pipes (Cody-Waite: x = n + f, |f| <= 1/2; degree-3 minimax of 2^f, relative error 7.5e-5 — a sixth of
+// the fp16 rounding P gets anyway; 2^n through the exponent field).  Used for a compile-time share of the scores so that the
+// two softmax warps of an SM sub-partition do not queue on its one MUFU (16 ex2 / clk / SM is this kernel's tightest floor).
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -125.0f);                               // masked keys (-inf): 2^-125, which rounds to 0 in fp16 and in the row sum
+  const float r = x + 12582912.0f;                     // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(f, 5.517137796e-02f, 2.426112145e-01f);
+  p = fmaf(p, f, 6.932610273e-01f);
+  p = fmaf(p, f, 9.999280572e-01f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 issue two fp32 operations per instruction; FMNMX3 is a three-input maximum): the
+// softmax warps are instruction-issue-bound (measured: every instruction added to the exp2 pass lengthens the kernel by its
+// issue slot), so the passes are written in the fewest instructions per score the ISA offers
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// which of the 32 scores of a chunk take the polynomial: POLY 0 none, 1 = 1/4, 2 = 1/2, 3 = 3/8
+template <int POLY>
+__device__ __forceinline__ constexpr bool use_poly(int e) {
+  return POLY == 1 ? (e & 3) == 3 : POLY == 2 ? (e & 1) == 1 : POLY == 3 ? ((e & 7) == 1 || (e & 7) == 4 || (e & 7) == 7) : false;
+}
+
+template <int POLY>
 __global__ void __launch_bounds__(384, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_constant__ CUtensorMap map_32,
                      const __grid_constant__ CUtensorMap map_o64, const __grid_constant__ CUtensorMap map_o32, const Attn3Args a) {
@@ -265,10 +311,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
         else tmem_ld_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(nxt));      // first chunk of pass 2
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]) + bias[c * 32 + i]);
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t sb2 = add_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])),
+                                           *reinterpret_cast<const uint64_t*>(bias + c * 32 + 2 * i));
+            float s0, s1;
+            unpack_f32x2(sb2, s0, s1);
+            mx = max3(mx, s0, s1);
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+          for (int i = 0; i < 16; ++i) mx = max3(mx, __uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
         }
       }
       mx *= a.scale_log2;                                     // -inf stays -inf
@@ -299,7 +351,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       // ---- pass 2: p = exp2(s*scale - m), row sum, pack to fp16 and write P over the S columns already consumed.
       // BN/32 is even, so pass 2 starts in buffer va (prefetched above) and alternates like pass 1.
-      float sum = 0.f;
+      // per PAIR of scores: one FFMA2 (scale, subtract the reference), two MUFU.EX2, one FADD2 (two running sums), one F2FP
+      uint64_t sum2 = pack_f32x2(0.f, 0.f);
+      const uint64_t scale2 = pack_f32x2(a.scale_log2, a.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         tmem_ld_wait();
@@ -309,11 +363,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
         uint32_t ph[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float t0 = fmaf(__uint_as_float(cur[2 * i]), a.scale_log2, neg_m);
-          float t1 = fmaf(__uint_as_float(cur[2 * i + 1]), a.scale_log2, neg_m);
-          if (masked) { t0 += bias[c * 32 + 2 * i]; t1 += bias[c * 32 + 2 * i + 1]; }
-          const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
-          sum += p0 + p1;
+          uint64_t t2 = fma_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), scale2, negm2);
+          if (masked) t2 = add_f32x2(t2, *reinterpret_cast<const uint64_t*>(bias + c * 32 + 2 * i));
+          float t0, t1;
+          unpack_f32x2(t2, t0, t1);
+          const float p0 = use_poly<POLY>(2 * i) ? exp2_poly3(t0) : fast_exp2(t0);
+          const float p1 = use_poly<POLY>(2 * i + 1) ? exp2_poly3(t1) : fast_exp2(t1);
+          sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
           __half2 hh = __floats2half2_rn(p0, p1);
           ph[i] = *reinterpret_cast<uint32_t*>(&hh);
         }
@@ -321,7 +377,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_co
         // in flight is above them too
         tmem_st_32x16(t_s + c * 16, ph);
       }
-      l_run += sum;
+      {
+        float s0, s1;
+        unpack_f32x2(sum2, s0, s1);
+        l_run += s0 + s1;
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -410,6 +470,21 @@ static int make_map3c(CUtensorMap* m, const void* base, int batch, int seq, int 
   return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
 }
 
+template <int POLY>
+static int launch_tc3(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& m64, const CUtensorMap& m32,
+                      const CUtensorMap& o64, const CUtensorMap& o32, const Attn3Args& a) {
+  static PerDeviceMax smem_max;
+  if (smem_max.need(smem)) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return (int)e;
+    smem_max.set(smem);
+  }
+  cudaError_t le = launch_pdl(attention_tc3_kernel<POLY>, dim3(grid), dim3(384), smem, stream, m64, m32, o64, o32, a);
+  if (le != cudaSuccess) return (int)le;
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                         cudaStream_t stream) {
   using namespace t3;
@@ -431,18 +506,14 @@ int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch
   if ((rc = make_map3c(&m32, qkv, batch, seq, ld, 32, BM, false))) return rc;
   if ((rc = make_map3c(&o64, out, batch, seq, heads * dh, 64, 32, true))) return rc;      // per-warp store boxes: 32 rows
   if ((rc = make_map3c(&o32, out, batch, seq, heads * dh, 32, 32, false))) return rc;
-  static PerDeviceMax smem_max;
-  if (smem_max.need(smem)) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e) return (int)e;
-    smem_max.set(smem);
-  }
   int grid = num_sms();
   if (grid > a.n_items) grid = a.n_items;
-  cudaError_t le = launch_pdl(attention_tc3_kernel, dim3(grid), dim3(384), smem, stream, m64, m32, o64, o32, a);
-  if (le != cudaSuccess) return (int)le;
-  count_launch();
-  return (int)cudaGetLastError();
+  switch (opts().attn_poly) {
+    case 1: return launch_tc3<1>(grid, smem, stream, m64, m32, o64, o32, a);
+    case 2: return launch_tc3<2>(grid, smem, stream, m64, m32, o64, o32, a);
+    case 3: return launch_tc3<3>(grid, smem, stream, m64, m32, o64, o32, a);
+    default: return launch_tc3<0>(grid, smem, stream, m64, m32, o64, o32, a);
+  }
 }
 
 }  // namespace caco

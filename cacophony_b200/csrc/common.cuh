@@ -33,8 +33,26 @@ struct PerDeviceMax {                  // largest value already configured on ea
   void set(size_t v) { cur[current_device()] = v; }
 };
 
-// programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch) for the tower kernels; 0 = ordinary stream order
-extern int g_pdl;
+// Execution options.  A model handle owns one set (caco_model_set_option) and installs it for the duration of each of its
+// calls on the calling thread; op-level C-ABI calls outside a handle use the library defaults (caco_set_default_option).
+struct Options {
+  int pdl = 1;              // programmatic dependent launch of the tower kernels (ptx.cuh: pdl_wait / pdl_launch)
+  int gemm_variant = 0;     // 0 = auto, else CACO_GEMM_*
+  int resid_red = 1;        // in-place residual GEMMs add through the L2 (red.global.add.v4.f32)
+  int attn_poly = 0;        // audio attention: share of the exp2 evaluated on the FMA pipe (0 none, 1 = 1/4, 2 = 1/2, 3 = 3/8)
+  int audio_chunk_rows = 131072;   // token rows per pass of the audio tower (larger batches are chunked)
+  int text_chunk_rows = 131072;
+  int split_weights = 0;    // precision mode: GEMM weights as fp16 hi + lo (two accumulating MMA passes)
+};
+extern Options g_default_opts;
+extern thread_local const Options* tl_opts;
+inline const Options& opts() { return tl_opts ? *tl_opts : g_default_opts; }
+struct OptionsScope {       // RAII: a handle's options are current on this thread while one of its calls enqueues work
+  const Options* prev;
+  explicit OptionsScope(const Options* o) : prev(tl_opts) { tl_opts = o; }
+  ~OptionsScope() { tl_opts = prev; }
+};
+int set_option(Options& o, const char* name, int value);   // 0 ok, CACO_ERR_ARG unknown name / bad value
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -46,16 +64,17 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = opts().pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // op-level entry points implemented across the .cu files (C++ side of the C ABI)
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
-             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream);
+             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream, int a_k = 0);
 int frontend(const float* wave, const int* lengths, int batch, int n_samples, int max_patches, float* patches,
              void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream);
 int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
+int cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
               int dim, cudaStream_t stream);
 int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,

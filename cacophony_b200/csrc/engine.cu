@@ -53,6 +53,10 @@ struct caco_model {
 
   void* ws[2] = {nullptr, nullptr};      // [0] audio tower, [1] text tower: the towers may run on different streams
   size_t ws_bytes[2] = {0, 0};
+  int device = -1;                       // the device the arenas / workspaces live on (a handle follows its model's .to())
+  int packed_split = 0;                  // layout of arena16: 0 = [N, K] fp16, 1 = [N, 2K] fp16 hi | lo (split_weights)
+  uint64_t generation = 0;               // bumped whenever a pointer a captured CUDA graph may have baked in is released
+  caco::Options opt;                     // per-handle execution options (caco_model_set_option)
 };
 
 namespace caco {
@@ -64,12 +68,27 @@ static const float* need(caco_model* m, const std::string& key, int64_t numel, i
   return it->second.p;
 }
 
+static void free_ws(caco_model* m, int which) {
+  if (!m->ws[which]) return;
+  cudaDeviceSynchronize();
+  cudaFree(m->ws[which]);
+  m->ws[which] = nullptr;
+  m->ws_bytes[which] = 0;
+  ++m->generation;
+}
 static int ensure_ws(caco_model* m, int which, size_t bytes) {
   if (bytes <= m->ws_bytes[which]) return 0;
-  if (m->ws[which]) { cudaDeviceSynchronize(); cudaFree(m->ws[which]); m->ws[which] = nullptr; m->ws_bytes[which] = 0; }
+  free_ws(m, which);
   cudaError_t e = cudaMalloc(&m->ws[which], bytes);
   if (e != cudaSuccess) return (int)e;
   m->ws_bytes[which] = bytes;
+  return 0;
+}
+// every entry point: the handle must be used on the device it was packed on (its arenas and workspaces live there)
+static int check_device(const caco_model* m) {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != m->device) { set_err("model packed on another device than the current one%s", ""); return CACO_ERR_STATE; }
   return 0;
 }
 
@@ -82,26 +101,39 @@ static int pack(caco_model* m, cudaStream_t st) {
   const int64_t D = c.hidden, F = c.ffn, P = c.patch_dim;
   int rc = 0;
   // ---- sizes
+  const int split = m->opt.split_weights ? 1 : 0;
   const int64_t per_layer = 3 * D * D + D * D + 2 * F * D;
-  const int64_t n16 = P * D + per_layer * (c.audio_layers + c.text_layers);
+  const int64_t n16 = (P * D + per_layer * (c.audio_layers + c.text_layers)) * (split ? 2 : 1);
   const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * D + 4 * 64;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (m->device != cur) {                // first pack, or the model moved to another GPU: nothing of the old device is kept
+    free_ws(m, 0);
+    free_ws(m, 1);
+    m->device = cur;
+  }
+  m->packed = false;
+  if (m->arena16 || m->arena32) { cudaDeviceSynchronize(); ++m->generation; }
   if (m->arena16) cudaFree(m->arena16);
   if (m->arena32) cudaFree(m->arena32);
+  m->arena16 = nullptr;
+  m->arena32 = nullptr;
   cudaError_t e = cudaMalloc(&m->arena16, n16 * sizeof(__half));
   if (e) return (int)e;
   e = cudaMalloc(&m->arena32, n32 * sizeof(float));
   if (e) return (int)e;
   __half* p16 = m->arena16;
   float* p32 = m->arena32;
-  auto take16 = [&](const float* src, int64_t n) -> const __half* {
+  // nn.Linear.weight [rows, K] fp32 -> fp16 [rows, K], or in split mode [rows, 2K] = fp16(w) | fp16(w - fp16(w))
+  auto take16 = [&](const float* src, int64_t n, int64_t K) -> const __half* {
     __half* dst = p16;
-    p16 += n;
-    if (src && rc == 0) rc = cast_f32_f16(src, dst, n, st);
+    p16 += n * (split ? 2 : 1);
+    if (src && rc == 0) rc = split ? cast_f32_f16_split(src, dst, n / K, K, st) : cast_f32_f16(src, dst, n, st);
     return dst;
   };
   // ---- audio tower (key names: SURVEY.md §8b)
   const std::string A = "audio_module.";
-  m->in_w = take16(need(m, A + "input_proj.weight", D * P, &rc), D * P);
+  m->in_w = take16(need(m, A + "input_proj.weight", D * P, &rc), D * P, P);
   m->in_b = need(m, A + "input_proj.bias", D, &rc);
   m->freq_emb = need(m, A + "freq_positional_embedding", (int64_t)c.n_freq * D, &rc);
   m->an_g = need(m, A + "norm.weight", D, &rc);
@@ -114,13 +146,13 @@ static int pack(caco_model* m, cudaStream_t st) {
     l.ln1_b = need(m, L + "norm1.bias", D, &rc);
     l.ln2_g = need(m, L + "norm2.weight", D, &rc);
     l.ln2_b = need(m, L + "norm2.bias", D, &rc);
-    l.qkv_w = take16(need(m, L + "attn.in_proj_weight", 3 * D * D, &rc), 3 * D * D);
+    l.qkv_w = take16(need(m, L + "attn.in_proj_weight", 3 * D * D, &rc), 3 * D * D, D);
     l.qkv_b = need(m, L + "attn.in_proj_bias", 3 * D, &rc);
-    l.out_w = take16(need(m, L + "attn.out_proj.weight", D * D, &rc), D * D);
+    l.out_w = take16(need(m, L + "attn.out_proj.weight", D * D, &rc), D * D, D);
     l.out_b = need(m, L + "attn.out_proj.bias", D, &rc);
-    l.fc1_w = take16(need(m, L + "mlp.fc1.weight", F * D, &rc), F * D);
+    l.fc1_w = take16(need(m, L + "mlp.fc1.weight", F * D, &rc), F * D, D);
     l.fc1_b = need(m, L + "mlp.fc1.bias", F, &rc);
-    l.fc2_w = take16(need(m, L + "mlp.fc2.weight", D * F, &rc), D * F);
+    l.fc2_w = take16(need(m, L + "mlp.fc2.weight", D * F, &rc), D * F, F);
     l.fc2_b = need(m, L + "mlp.fc2.bias", D, &rc);
   }
   if (rc) return rc;
@@ -156,7 +188,7 @@ static int pack(caco_model* m, cudaStream_t st) {
     float* qkvb = p32;
     const char* nm[3] = {"query", "key", "value"};
     for (int j = 0; j < 3; ++j) {
-      take16(need(m, L + "attention.self." + nm[j] + ".weight", D * D, &rc), D * D);
+      take16(need(m, L + "attention.self." + nm[j] + ".weight", D * D, &rc), D * D, D);
       const float* b = need(m, L + "attention.self." + nm[j] + ".bias", D, &rc);
       if (rc) return rc;
       e = cudaMemcpyAsync(p32, b, D * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -165,13 +197,13 @@ static int pack(caco_model* m, cudaStream_t st) {
     }
     l.qkv_w = qkv;
     l.qkv_b = qkvb;
-    l.o_w = take16(need(m, L + "attention.output.dense.weight", D * D, &rc), D * D);
+    l.o_w = take16(need(m, L + "attention.output.dense.weight", D * D, &rc), D * D, D);
     l.o_b = need(m, L + "attention.output.dense.bias", D, &rc);
     l.ln1_g = need(m, L + "attention.output.LayerNorm.weight", D, &rc);
     l.ln1_b = need(m, L + "attention.output.LayerNorm.bias", D, &rc);
-    l.fc1_w = take16(need(m, L + "intermediate.dense.weight", F * D, &rc), F * D);
+    l.fc1_w = take16(need(m, L + "intermediate.dense.weight", F * D, &rc), F * D, D);
     l.fc1_b = need(m, L + "intermediate.dense.bias", F, &rc);
-    l.fc2_w = take16(need(m, L + "output.dense.weight", D * F, &rc), D * F);
+    l.fc2_w = take16(need(m, L + "output.dense.weight", D * F, &rc), D * F, F);
     l.fc2_b = need(m, L + "output.dense.bias", D, &rc);
     l.ln2_g = need(m, L + "output.LayerNorm.weight", D, &rc);
     l.ln2_b = need(m, L + "output.LayerNorm.bias", D, &rc);
@@ -193,6 +225,21 @@ static int pack(caco_model* m, cudaStream_t st) {
     CK(fold_query(query, kw, kb, 1.0f / sqrtf((float)D), m->t_u, m->t_c, 1, (int)D, (int)D, st));   // roberta.py:259
   }
   m->packed = true;
+  m->packed_split = split;
+  return 0;
+}
+
+// y = epilogue(A[M,K] · W^T) with W as packed by pack(): [N, K], or [N, 2K] hi | lo in split-weight mode (A re-read per term)
+static int lin(const caco_model* m, const __half* A, int lda, const __half* W, int K, const float* bias, const float* resid,
+               int ldr, void* out, int ldo, int M, int N, int epi, cudaStream_t st) {
+  const int t = m->packed_split ? 2 : 1;
+  return gemm_f16(A, lda, W, K * t, bias, resid, ldr, out, ldo, M, N, K * t, epi, 0, 0, st, K);
+}
+// entry-point prologue: right device, weights packed in the layout the handle's options ask for
+static int ready(caco_model* m, cudaStream_t st) {
+  if (!m || !m->packed) return CACO_ERR_STATE;
+  CK(check_device(m));
+  if ((m->opt.split_weights ? 1 : 0) != m->packed_split) CK(pack(m, st));
   return 0;
 }
 
@@ -227,20 +274,20 @@ static int audio_chunk(caco_model* m, const float* patches, const __half* patche
   // x = pos(t) + freq_emb[f] written first (no read), then the projection accumulates onto it in place (L2 reductions):
   // one pass over x less than project-then-add
   CK(audio_add_pos(x, t_inds, f_inds, m->freq_emb, c.n_freq, Ri, D, 1, st));
-  CK(gemm_f16(patches16 ? patches16 : p16, P, m->in_w, P, m->in_b, x, D, x, D, Ri, D, P, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+  CK(lin(m, patches16 ? patches16 : p16, P, m->in_w, P, m->in_b, x, D, x, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
   // pre-LN blocks (mae.py:80-99)
   for (int i = 0; i < c.audio_layers; ++i) {
     const caco_model::ALayer& l = m->al[i];
-    CK(layernorm(x, l.ln1_g, l.ln1_b, c.ln_eps, nullptr, h16, Ri, D, st));
-    CK(gemm_f16(h16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, D, CACO_EPI_BIAS_F16, 0, 0, st));
+    CK(layernorm(x, l.ln1_g, l.ln1_b, c.audio_ln_eps, nullptr, h16, Ri, D, st));
+    CK(lin(m, h16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, CACO_EPI_BIAS_F16, st));
     CK(attention_audio(qkv, mask, att, B, S, c.audio_heads, D / c.audio_heads, st));
-    CK(gemm_f16(att, D, l.out_w, D, l.out_b, x, D, x, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
-    CK(layernorm(x, l.ln2_g, l.ln2_b, c.ln_eps, nullptr, h16, Ri, D, st));
-    CK(gemm_f16(h16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, D, CACO_EPI_BIAS_SILU_F16, 0, 0, st));
-    CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, x, D, x, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+    CK(lin(m, att, D, l.out_w, D, l.out_b, x, D, x, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
+    CK(layernorm(x, l.ln2_g, l.ln2_b, c.audio_ln_eps, nullptr, h16, Ri, D, st));
+    CK(lin(m, h16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, CACO_EPI_BIAS_SILU_F16, st));
+    CK(lin(m, mlp, F, l.fc2_w, F, l.fc2_b, x, D, x, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
   }
   // final LN (mae.py:147) fused into the pooler's pass over the rows (caco.py:41-79)
-  CK(attn_pool(x, mask, m->a_u, m->a_c, m->an_g, m->an_b, c.ln_eps, hidden_out, pooled, B, S, c.pool_heads, D, st));
+  CK(attn_pool(x, mask, m->a_u, m->a_c, m->an_g, m->an_b, c.audio_ln_eps, hidden_out, pooled, B, S, c.pool_heads, D, st));
   const int dh = D / c.pool_heads;
   for (int h = 0; h < c.pool_heads; ++h)
     CK(sgemm_nt(pooled + (size_t)h * D, c.pool_heads * D, m->ap_vw + (size_t)h * dh * D, D, m->ap_vb + h * dh, 1.0f,
@@ -254,11 +301,12 @@ static int audio_chunk(caco_model* m, const float* patches, const __half* patche
 static int audio_embedding(caco_model* m, const float* patches, const __half* patches16, const float* t_inds,
                            const float* f_inds, const float* mask, int B, int S, int normalize, float* emb_out,
                            float* hidden_out, cudaStream_t st) {
-  if (!m || !m->packed) return CACO_ERR_STATE;
+  CK(ready(m, st));
+  OptionsScope scope(&m->opt);
   if ((!patches && !patches16) || !t_inds || !f_inds || !mask || !emb_out || B <= 0 || S <= 0) return CACO_ERR_ARG;
   const caco_config& c = m->cfg;
-  // bound the workspace: at most ~131072 token rows per pass (256 clips of 500 tokens)
-  int chunk = (int)(131072 / S);
+  // bound the workspace: at most audio_chunk_rows token rows per pass (default 131072 = 256 clips of 500 tokens)
+  int chunk = m->opt.audio_chunk_rows / S;
   if (chunk < 1) chunk = 1;
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -273,11 +321,12 @@ static int audio_embedding(caco_model* m, const float* patches, const __half* pa
 // ---------------------------------------------------------------------------------------- text tower
 static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, const int64_t* pids, int B, int T,
                           int normalize, float* emb_out, float* hidden_out, cudaStream_t st) {
-  if (!m || !m->packed) return CACO_ERR_STATE;
+  CK(ready(m, st));
+  OptionsScope scope(&m->opt);
   if (!ids || !mask || !emb_out || B <= 0 || T <= 0) return CACO_ERR_ARG;
   const caco_config& c = m->cfg;
   const int D = c.hidden, F = c.ffn;
-  int chunk = 131072 / T;
+  int chunk = m->opt.text_chunk_rows / T;
   if (chunk < 1) chunk = 1;
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -308,13 +357,13 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
                      c.max_pos, st));
     for (int i = 0; i < c.text_layers; ++i) {   // post-LN blocks (roberta.py:191-215)
       const caco_model::TLayer& l = m->tl[i];
-      CK(gemm_f16(x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, D, CACO_EPI_BIAS_F16, 0, 0, st));
+      CK(lin(m, x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, CACO_EPI_BIAS_F16, st));
       CK(attention_text(qkv, mask_c, att, nb, T, c.text_heads, D / c.text_heads, st));
       // the residual operand is dead after the add (post-LN), so the sum is accumulated in place (L2 reductions)
-      CK(gemm_f16(att, D, l.o_w, D, l.o_b, x, D, x, D, Ri, D, D, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(lin(m, att, D, l.o_w, D, l.o_b, x, D, x, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
       CK(layernorm(x, l.ln1_g, l.ln1_b, c.ln_eps, a, a16, Ri, D, st));
-      CK(gemm_f16(a16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, D, CACO_EPI_BIAS_GELU_F16, 0, 0, st));
-      CK(gemm_f16(mlp, F, l.fc2_w, F, l.fc2_b, a, D, a, D, Ri, D, F, CACO_EPI_BIAS_RESID_F32, 0, 0, st));
+      CK(lin(m, a16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, CACO_EPI_BIAS_GELU_F16, st));
+      CK(lin(m, mlp, F, l.fc2_w, F, l.fc2_b, a, D, a, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
       CK(layernorm(a, l.ln2_g, l.ln2_b, c.ln_eps, x, x16, Ri, D, st));
     }
     if (hidden_out) {
@@ -339,12 +388,14 @@ const char* caco_last_error(void) { return caco::g_err; }
 int caco_model_create(const caco_config* cfg, caco_model** out) {
   if (!cfg || !out) return CACO_ERR_ARG;
   if (cfg->hidden % 128 || cfg->hidden > 1024 || cfg->hidden % cfg->audio_heads || cfg->hidden % cfg->text_heads ||
-      cfg->hidden % cfg->pool_heads || cfg->pool_heads > 4)
+      cfg->hidden % cfg->pool_heads || cfg->pool_heads > 8)      // caco/load_model.py:47 uses 8 pooler heads, caco.py:292 uses 2
     return CACO_ERR_ARG;
   const int adh = cfg->hidden / cfg->audio_heads;
   if ((adh != 96 && adh != 64) || cfg->hidden / cfg->text_heads != 64) return CACO_ERR_ARG;
   caco_model* m = new caco_model();
   m->cfg = *cfg;
+  if (m->cfg.audio_ln_eps <= 0.f) m->cfg.audio_ln_eps = 1e-5f;   // nn.LayerNorm's default (mae.py:68,76,123)
+  m->opt = caco::g_default_opts;
   *out = m;
   return 0;
 }
@@ -372,6 +423,13 @@ int caco_model_pack(caco_model* m, void* stream) {
   return caco::pack(m, (cudaStream_t)stream);
 }
 
+int caco_model_set_option(caco_model* m, const char* name, int value) {
+  if (!m) return CACO_ERR_ARG;
+  return caco::set_option(m->opt, name, value);
+}
+
+uint64_t caco_model_generation(const caco_model* m) { return m ? m->generation : 0; }
+
 int caco_model_audio_embedding(caco_model* m, const float* patches, const float* time_inds, const float* freq_inds,
                                const float* mask, int batch, int seq, int normalize, float* emb_out, float* hidden_out,
                                void* stream) {
@@ -389,7 +447,8 @@ int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* ma
 // patches are never written on this path.
 static int encode_audio_impl(caco_model* m, const float* wave, const int* lengths, int batch, int stride, int max_patches,
                              int normalize, float* emb_out, float* hidden_out, float* mask_out, cudaStream_t st) {
-  if (!m || !m->packed) return CACO_ERR_STATE;
+  CK(caco::ready(m, st));
+  caco::OptionsScope scope(&m->opt);
   if (!wave || !emb_out || batch <= 0 || stride <= 0 || max_patches <= 0) return CACO_ERR_ARG;
   const size_t R = (size_t)batch * max_patches;
   uint8_t* buf = nullptr;

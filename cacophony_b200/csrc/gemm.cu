@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -40,8 +41,12 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// number of 4-element fp16 stores (GEMM epilogues, LayerNorm) that had to clamp a value to the fp16 range since the last reset
+__device__ unsigned int g_saturated = 0;
+
 struct GemmArgs {
   int M, N, K;
+  int a_kb;          // k-blocks of A before its column coordinate wraps (split-weight mode: W = [hi | lo] along K, A re-read)
   int ldo, ldr;
   const float* bias;
   const float* resid;
@@ -156,22 +161,24 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int mb = tile / g.num_n_blocks, nb = tile % g.num_n_blocks;
       const int row_a = (mb * CG + (int)cta_rank) * BM;
       const int row_b = nb * BN + (int)cta_rank * Cfg::B_ROWS;
+      int ka = 0;     // A's k-block (wraps in split-weight mode)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
         if (lane == 0) {
           const uint32_t full = bar_full + 8 * stage;
           if constexpr (CG == 1) {
             mbar_expect_tx(full, Cfg::STAGE_BYTES);
-            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
+            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, ka * BK, row_a);
             tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
           } else {
             // the LEADER's barrier counts the bytes of both CTAs; the peer's loads complete_tx on it remotely.  (The
             // peer can only be one phase ahead after its own empty barrier fired, i.e. after the leader's phase closed.)
             if (leader) mbar_expect_tx(full, CG * Cfg::STAGE_BYTES);
-            tma_load_2d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, kb * BK, row_a);
+            tma_load_2d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, full, ka * BK, row_a);
             tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &tmap_b, full, kb * BK, row_b);
           }
         }
+        if (++ka == g.a_kb) ka = 0;
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -313,6 +320,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             } else if constexpr (kF32Out) {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + (size_t)grow * g.ldo + gcol) = a;
             } else {
+              // fp16 operand copy: a value past the fp16 range is clamped (not +-inf) and reported (caco_saturation_count)
+              if (fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))) > 65504.0f) {
+                a.x = fminf(fmaxf(a.x, -65504.0f), 65504.0f); a.y = fminf(fmaxf(a.y, -65504.0f), 65504.0f);
+                a.z = fminf(fmaxf(a.z, -65504.0f), 65504.0f); a.w = fminf(fmaxf(a.w, -65504.0f), 65504.0f);
+                atomicAdd(&g_saturated, 1u);
+              }
               __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
               uint2 u;
               u.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -367,15 +380,27 @@ int make_tmap_f16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
 }
 
-int g_pdl = 1;
-static int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
+Options g_default_opts;
+thread_local const Options* tl_opts = nullptr;
+int set_option(Options& o, const char* name, int value) {
+  if (!name) return CACO_ERR_ARG;
+  const std::string n(name);
+  if (n == "pdl") o.pdl = value != 0;
+  else if (n == "gemm_variant") { if (value < 0 || value > CACO_GEMM_CG2_N256_E16) return CACO_ERR_ARG; o.gemm_variant = value; }
+  else if (n == "resid_red") o.resid_red = value != 0;
+  else if (n == "attn_poly") { if (value < 0 || value > 3) return CACO_ERR_ARG; o.attn_poly = value; }
+  else if (n == "audio_chunk_rows") { if (value < 1) return CACO_ERR_ARG; o.audio_chunk_rows = value; }
+  else if (n == "text_chunk_rows") { if (value < 1) return CACO_ERR_ARG; o.text_chunk_rows = value; }
+  else if (n == "split_weights") o.split_weights = value != 0;
+  else return CACO_ERR_ARG;
+  return 0;
+}
+
+int num_sms() {                       // per device (a process may drive several GPUs)
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev];
 }
 
 template <int CG, int BN, int STAGES, int EPI_WARPS, int EPI>
@@ -407,7 +432,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 2 : 1;
+  cfg.numAttrs = opts().pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
   count_launch();
   return (int)e;
@@ -428,8 +453,6 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, con
 
 int launch_variant(int variant, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int max_ctas,
                    cudaStream_t stream);
-static int g_gemm_variant = 0;  // 0 = auto
-static int g_resid_red = 1;     // in-place residual GEMMs use L2 reductions (0: load/add/store, for A/B measurements)
 
 // ---- optional live profiling (bench.py's roofline leg): CUDA events around every GEMM launch on its stream
 struct GemmProf {
@@ -441,8 +464,11 @@ struct GemmProf {
 static GemmProf g_prof;
 
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr, void* out,
-             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream) {
+             int ldo, int M, int N, int K, int epi, int variant, int max_ctas, cudaStream_t stream, int a_k) {
   if (M <= 0 || N <= 0 || K <= 0) return CACO_ERR_ARG;
+  // a_k: K extent of A when W carries several K-concatenated terms for the same A (split weights: W = [hi | lo], K = 2 a_k)
+  if (a_k <= 0) a_k = K;
+  if (a_k != K && ((a_k % BK) || (K % a_k))) return CACO_ERR_ARG;
   if ((N & 3) || (K & 7) || (ldo & 3)) return CACO_ERR_ARG;
   if (epi == CACO_EPI_BIAS_RESID_F32 && (resid == nullptr || (ldr & 3))) return CACO_ERR_ARG;
   const bool f16_out = (epi == CACO_EPI_BIAS_F16 || epi == CACO_EPI_BIAS_SILU_F16 || epi == CACO_EPI_BIAS_GELU_F16);
@@ -454,18 +480,18 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
     // machine better than CTA pairs (measured at M = 8192: QKV 28.0 vs 34.8 us, out 20.1 vs 25.4, fc1 50.4 vs 64.7, fc2 44.4 vs
     // 55.4 us).  Otherwise CTA-pair 256x256 tiles; activation epilogues get 16 epilogue warps.
     const long long pair_tiles = (((long long)M + 255) / 256) * (((long long)N + 255) / 256);
-    variant = g_gemm_variant ? g_gemm_variant
+    variant = opts().gemm_variant ? opts().gemm_variant
               : (pair_tiles < 8 * (num_sms() / 2)) ? CACO_GEMM_CG1_N256
               : ((epi == CACO_EPI_BIAS_SILU_F16 || epi == CACO_EPI_BIAS_GELU_F16) ? CACO_GEMM_CG2_N256_E16 : CACO_GEMM_CG2_N256);
   }
   const int cg = (variant == CACO_GEMM_CG2_N256 || variant == CACO_GEMM_CG2_N256_E16) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;
   GemmArgs g;
-  g.M = M; g.N = N; g.K = K; g.ldo = ldo; g.ldr = ldr; g.bias = bias; g.resid = resid; g.out = out;
+  g.M = M; g.N = N; g.K = K; g.a_kb = (a_k + BK - 1) / BK; g.ldo = ldo; g.ldr = ldr; g.bias = bias; g.resid = resid; g.out = out;
   g.num_m_blocks = (M + BM * cg - 1) / (BM * cg);
   g.num_n_blocks = (N + bn - 1) / bn;
   CUtensorMap ta, tb;
-  int rc = make_tmap_f16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+  int rc = make_tmap_f16(&ta, A, (uint64_t)M, (uint64_t)a_k, (uint64_t)lda, BM);
   if (rc) return rc;
   rc = make_tmap_f16(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / cg));
   if (rc) return rc;
@@ -483,7 +509,7 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
     g_prof.flops[slot] = 2.0 * (double)M * (double)N * (double)K;
     cudaEventRecord(g_prof.ev[slot].first, stream);
   }
-  if (epi == CACO_EPI_BIAS_RESID_F32 && resid == out && ldr == ldo && g_resid_red) epi = EPI_RESID_INPLACE;
+  if (epi == CACO_EPI_BIAS_RESID_F32 && resid == out && ldr == ldo && opts().resid_red) epi = EPI_RESID_INPLACE;
   rc = launch_variant(variant, epi, ta, tb, g, max_ctas, stream);
   if (prof) cudaEventRecord(g_prof.ev[slot].second, stream);
   return rc;
@@ -504,12 +530,20 @@ int launch_variant(int variant, int epi, const CUtensorMap& ta, const CUtensorMa
 
 extern "C" int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid,
                              int ldr, void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream) {
-  return caco::gemm_f16(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, epi, variant, 0, (cudaStream_t)stream);
+  return caco::gemm_f16(A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, epi, variant, 0, (cudaStream_t)stream, 0);
 }
-
-extern "C" void caco_set_gemm_variant(int variant) { caco::g_gemm_variant = variant; }
-extern "C" void caco_set_gemm_resid_red(int enable) { caco::g_resid_red = enable; }
-extern "C" void caco_set_pdl(int enable) { caco::g_pdl = enable; }
+extern "C" int caco_gemm_f16_wsplit(const void* A, int lda, const void* W2, int ldw, const float* bias, const float* resid,
+                                    int ldr, void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream) {
+  return caco::gemm_f16(A, lda, W2, ldw, bias, resid, ldr, out, ldo, M, N, 2 * K, epi, variant, 0, (cudaStream_t)stream, K);
+}
+extern "C" int caco_set_default_option(const char* name, int value) { return caco::set_option(caco::g_default_opts, name, value); }
+extern "C" unsigned int caco_saturation_count(int reset) {
+  unsigned int v = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&v, caco::g_saturated, sizeof(v));
+  if (reset) { const unsigned int z = 0; cudaMemcpyToSymbol(caco::g_saturated, &z, sizeof(z)); }
+  return v;
+}
 
 extern "C" void caco_gemm_profile(int enable) {
   caco::g_prof.on = enable != 0;

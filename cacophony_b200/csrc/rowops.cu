@@ -41,6 +41,31 @@ int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// split-weight packing: dst[r, 0:K] = fp16(w), dst[r, K:2K] = fp16(w - fp16(w))   (K % 4 == 0)
+__global__ void cast_f32_f16_split_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t rows, int64_t K) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= rows * K) return;
+  const int64_t r = i / K, k = i - r * K;
+  const float4 v = *reinterpret_cast<const float4*>(src + i);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __float2half_rn(f[j]);
+    lo[j] = __float2half_rn(f[j] - __half2float(hi[j]));
+  }
+  *reinterpret_cast<uint2*>(dst + r * 2 * K + k) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(dst + r * 2 * K + K + k) = *reinterpret_cast<const uint2*>(lo);
+}
+int cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K, cudaStream_t stream) {
+  if (!src || !dst || rows <= 0 || K <= 0 || (K & 3)) return CACO_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7)) return CACO_ERR_ALIGN;
+  const int64_t threads = rows * K / 4;
+  cast_f32_f16_split_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(src, (__half*)dst, rows, K);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ row helpers
 struct RowStats { float mean, rstd; };
 
@@ -230,7 +255,8 @@ template <int HEADS>
 __global__ void __launch_bounds__(POOL_THREADS)
 attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, const float* __restrict__ u,
                  const float* __restrict__ cvec, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-                 float* __restrict__ hid_out, float* __restrict__ pooled, int S, int dim) {
+                 float* __restrict__ hid_out, float* __restrict__ pooled, int S, int dim, int heads_total) {
+  // u / cvec / pooled already point at this launch's first head; heads_total = row stride of pooled in heads
   extern __shared__ float sm[];
   float* s_part = sm;                                   // [warps][HEADS][dim]
   __shared__ float s_m[POOL_WARPS][POOL_MAX_HEADS], s_l[POOL_WARPS][POOL_MAX_HEADS];
@@ -324,7 +350,7 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
     for (int h = 0; h < HEADS; ++h) {
       float a = 0.f;
       for (int w = 0; w < POOL_WARPS; ++w) a = fmaf(s_part[((size_t)w * HEADS + h) * dim + col], s_scale[w][h], a);
-      pooled[((size_t)b * HEADS + h) * dim + col] = a * s_inv[h];
+      pooled[((size_t)b * heads_total + h) * dim + col] = a * s_inv[h];
     }
   }
 }
@@ -332,7 +358,7 @@ attn_pool_kernel(const float* __restrict__ hid, const float* __restrict__ mask, 
 template <int HEADS>
 static int launch_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
                        const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int dim,
-                       cudaStream_t stream) {
+                       int heads_total, cudaStream_t stream) {
   const size_t smem = (size_t)POOL_WARPS * HEADS * dim * sizeof(float);
   if (smem > 200 * 1024) return CACO_ERR_ARG;
   static PerDeviceOnce attr_once;
@@ -341,7 +367,7 @@ static int launch_pool(const float* hid, const float* mask, const float* u, cons
     if (e) return (int)e;
     attr_once.done();
   }
-  attn_pool_kernel<HEADS><<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, dim);
+  attn_pool_kernel<HEADS><<<batch, POOL_THREADS, smem, stream>>>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, seq, dim, heads_total);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -349,15 +375,25 @@ static int launch_pool(const float* hid, const float* mask, const float* u, cons
 int attn_pool(const float* hid, const float* mask, const float* u, const float* c, const float* ln_gamma,
               const float* ln_beta, float ln_eps, float* hid_out, float* pooled, int batch, int seq, int heads, int dim,
               cudaStream_t stream) {
-  if (!hid || !mask || !u || !c || !pooled || batch <= 0 || seq <= 0 || heads <= 0 || heads > POOL_MAX_HEADS)
-    return CACO_ERR_ARG;
+  if (!hid || !mask || !u || !c || !pooled || batch <= 0 || seq <= 0 || heads <= 0 || heads > 16) return CACO_ERR_ARG;
   if ((dim % 128) || dim > 128 * ROW_MAX_V4) return CACO_ERR_ARG;
-  switch (heads) {
-    case 1: return launch_pool<1>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
-    case 2: return launch_pool<2>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
-    case 3: return launch_pool<3>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
-    default: return launch_pool<4>(hid, mask, u, c, ln_gamma, ln_beta, ln_eps, hid_out, pooled, batch, seq, dim, stream);
+  // up to POOL_MAX_HEADS heads share one pass over the rows (their running sums live in registers); more heads (the JAX
+  // configuration's 8, caco/load_model.py:47) take one pass per group of four.  The LayerNorm-ed rows are written once.
+  for (int h0 = 0; h0 < heads; h0 += POOL_MAX_HEADS) {
+    const int nh = heads - h0 < POOL_MAX_HEADS ? heads - h0 : POOL_MAX_HEADS;
+    const float* uu = u + (size_t)h0 * dim;
+    float* pp = pooled + (size_t)h0 * dim;
+    float* ho = h0 == 0 ? hid_out : nullptr;
+    int rc;
+    switch (nh) {
+      case 1: rc = launch_pool<1>(hid, mask, uu, c + h0, ln_gamma, ln_beta, ln_eps, ho, pp, batch, seq, dim, heads, stream); break;
+      case 2: rc = launch_pool<2>(hid, mask, uu, c + h0, ln_gamma, ln_beta, ln_eps, ho, pp, batch, seq, dim, heads, stream); break;
+      case 3: rc = launch_pool<3>(hid, mask, uu, c + h0, ln_gamma, ln_beta, ln_eps, ho, pp, batch, seq, dim, heads, stream); break;
+      default: rc = launch_pool<4>(hid, mask, uu, c + h0, ln_gamma, ln_beta, ln_eps, ho, pp, batch, seq, dim, heads, stream); break;
+    }
+    if (rc) return rc;
   }
+  return 0;
 }
 
 // fold a pooler's key projection into its (fixed) query: u[h,i] = sum_d qs[h,d] Wk[h*dh+d, i], c[h] = sum_d qs[h,d] bk[h*dh+d]
@@ -499,6 +535,9 @@ int caco_version(void) { return 100; }
 int caco_built_arch(void) { return 100; }
 int64_t caco_launch_count(void) { return caco::g_launches.load(); }
 int caco_cast_f32_f16(const float* src, void* dst, int64_t n, void* stream) { return caco::cast_f32_f16(src, dst, n, (cudaStream_t)stream); }
+int caco_cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K, void* stream) {
+  return caco::cast_f32_f16_split(src, dst, rows, K, (cudaStream_t)stream);
+}
 int caco_layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
                    int dim, void* stream) {
   return caco::layernorm(x, gamma, beta, eps, out_f32, out_f16, rows, dim, (cudaStream_t)stream);

@@ -202,6 +202,35 @@ class RobertaModel(nn.Module):
         self.pooler = AttentionPooler(config)
 
 
+class _DecoderLayer(RobertaLayer):     # roberta.py:181-215 with the cross-attention branch (:185-187)
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__(cfg)
+        self.crossattention = _Attention(cfg)
+
+
+class _DecoderEncoder(nn.Module):      # RobertaEncoder(config, has_cross_attention=True), roberta.py:218-224
+    def __init__(self, cfg: RobertaConfig):
+        super().__init__()
+        self.layers = nn.ModuleList([_DecoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+
+
+class RobertaDecoder(nn.Module):
+    """Parameter tree of the captioning head (roberta.py:329-373: layers with cross-attention + ``decoder_proj``), same
+    ``state_dict`` keys as the reference's, exported so ``from cacophony_b200 import *`` offers the reference's names and a
+    checkpoint's ``decoder_module.*`` tensors have somewhere to live.  Captioning is not on the inference hot path
+    (SURVEY.md 8, row f-4): there is no forward."""
+
+    def __init__(self, config: RobertaConfig):
+        super().__init__()
+        self.config = config
+        self.encoder = _DecoderEncoder(config)
+        self.decoder_proj = _Linear(config.hidden_size, config.vocab_size)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("cacophony_b200 implements the contrastive inference path; the captioning decoder is a "
+                                  "parameter container only")
+
+
 # ------------------------------------------------------------------------------------------------------
 # CACO
 # ------------------------------------------------------------------------------------------------------
@@ -225,6 +254,8 @@ class CACO(nn.Module):
         self.decoder_module = None       # caco.py:118-121: captioning head, not on this path
         self._handle: Optional[int] = None
         self._packed_key = None
+        self._side_stream = None
+        self._options: Dict[str, int] = {}
         self.eval()
 
     # ---- state handling ---------------------------------------------------------------------------
@@ -246,6 +277,38 @@ class CACO(nn.Module):
         except Exception:
             pass
 
+    # The C handle (packed weights, workspaces) belongs to ONE Python object: copies and unpickled models start without one
+    # and build their own at first use — never two objects destroying the same handle, never a copy running on the
+    # original's packed weights.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"], state["_packed_key"], state["_side_stream"] = None, None, None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._handle, self._packed_key, self._side_stream = None, None, None
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_handle", "_packed_key", "_side_stream") else copy.deepcopy(v, memo)
+        return new
+
+    # ---- execution options (per model; see caco_set_default_option in include/caco_b200.h for the names) -------------
+    def set_option(self, name: str, value: int) -> None:
+        """E.g. ``set_option("split_weights", 1)``: GEMM weights as fp16 hi + lo (two accumulating tensor-core passes, the
+        precision escape hatch of SURVEY.md 7.3), ``"audio_chunk_rows"``, ``"attn_poly"``, ``"pdl"``."""
+        self._options[name] = int(value)
+        if self._handle is not None:
+            L.check(L.load().caco_model_set_option(self._handle, name.encode(), int(value)), f"caco_model_set_option({name})")
+
+    def generation(self) -> int:
+        """Changes whenever the handle released device memory an earlier enqueued / captured call may reference."""
+        return 0 if self._handle is None else int(L.load().caco_model_generation(self._handle))
+
     def _device(self) -> torch.device:
         return self.logit_scale.device
 
@@ -261,10 +324,13 @@ class CACO(nn.Module):
             a, t = self.audio_config, self.text_config
             cfg = L.CacoConfig(a.hidden_size, a.intermediate_size, a.patch_size, a.num_layers, a.num_heads,
                                a.num_freq_patches, self.caco_config.num_attention_pool_heads, t.num_hidden_layers,
-                               t.num_attention_heads, t.vocab_size, t.max_position_embeddings, float(t.layer_norm_eps))
+                               t.num_attention_heads, t.vocab_size, t.max_position_embeddings, float(t.layer_norm_eps),
+                               1e-5)        # audio tower: nn.LayerNorm's default eps (mae.py:68,76,123)
             h = C.c_void_p()
             L.check(lib.caco_model_create(C.byref(cfg), C.byref(h)), "caco_model_create")
             self._handle = h.value
+            for name, value in self._options.items():
+                L.check(lib.caco_model_set_option(self._handle, name.encode(), value), f"caco_model_set_option({name})")
         with torch.cuda.device(dev):
             for k, v in sd.items():
                 if v.dtype != torch.float32 or not v.is_contiguous():
@@ -404,6 +470,13 @@ class CACO(nn.Module):
                                                         L.ptr(hid), L.ptr(mk), L.stream_ptr()), "caco_model_encode_audio_ex")
         return (emb, hid, mk) if return_hidden_state else emb
 
+    def side_stream(self) -> "torch.cuda.Stream":
+        """The stream the text tower runs on next to the audio tower (created on first use, follows the model's device)."""
+        dev = self._device()
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        return self._side_stream
+
     @torch.no_grad()
     def encode_text(self, text_input_ids: torch.Tensor, text_mask: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         return self.get_text_embedding(text_input_ids, text_mask, return_hidden_state=False, normalize=normalize)
@@ -416,8 +489,7 @@ class CACO(nn.Module):
         workspaces in the C handle).  Returns (audio_embeddings, text_embeddings)."""
         dev = self._device()
         self._ensure_packed()
-        if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
-            self._side_stream = torch.cuda.Stream(device=dev)
+        self.side_stream()
         cur = torch.cuda.current_stream(dev)
         ids = _as(text_input_ids, torch.int64, dev, "text_input_ids")
         mk = _as(text_mask, torch.float32, dev, "text_mask")

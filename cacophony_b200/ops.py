@@ -11,7 +11,29 @@ from typing import Optional, Tuple
 
 import torch
 
+import functools
+
 from . import _lib as L
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current (the library enqueues on the current device's
+    current stream), and require all tensor arguments to live on ONE device — a model on cuda:1 must work while cuda:0 is the
+    process's current device."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise ValueError(f"{fn.__name__}: tensor arguments live on different devices ({dev} and {a.device})")
+        if dev is None:
+            return fn(*args, **kwargs)          # argument validation below raises the proper error
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
@@ -26,6 +48,7 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+@_on_tensor_device
 def cast_f16(x: torch.Tensor) -> torch.Tensor:
     _need(x, torch.float32, "x")
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
@@ -33,6 +56,7 @@ def cast_f16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epi: int,
              resid: Optional[torch.Tensor] = None, variant: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """epilogue(a[M,K] @ w[N,K].T + bias); a, w fp16; out fp16 (EPI_*_F16) or fp32."""
@@ -63,6 +87,36 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epi
     return out
 
 
+@_on_tensor_device
+def cast_f16_split(w: torch.Tensor) -> torch.Tensor:
+    """w [N, K] fp32 -> [N, 2K] fp16 = fp16(w) | fp16(w - fp16(w)): the split-weight packing."""
+    _need(w, torch.float32, "w")
+    if w.dim() != 2:
+        raise ValueError("cast_f16_split: w must be [N, K]")
+    out = torch.empty((w.shape[0], 2 * w.shape[1]), dtype=torch.float16, device=w.device)
+    L.check(L.load().caco_cast_f32_f16_split(L.ptr(w), L.ptr(out), w.shape[0], w.shape[1], L.stream_ptr()),
+            "caco_cast_f32_f16_split")
+    return out
+
+
+@_on_tensor_device
+def gemm_f16_wsplit(a: torch.Tensor, w2: torch.Tensor, bias: Optional[torch.Tensor], epi: int,
+                    resid: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """epilogue(a[M,K] @ (hi + lo)[N,K].T + bias) with w2 = cast_f16_split(w) [N, 2K]."""
+    _need(a, torch.float16, "a")
+    _need(w2, torch.float16, "w2")
+    M, K = a.shape
+    N = w2.shape[0]
+    if w2.shape[1] != 2 * K:
+        raise ValueError("gemm_f16_wsplit: w2 must be [N, 2K]")
+    out_dtype = torch.float32 if epi in (L.EPI_BIAS_F32, L.EPI_BIAS_RESID_F32) else torch.float16
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    L.check(L.load().caco_gemm_f16_wsplit(L.ptr(a), K, L.ptr(w2), 2 * K, L.ptr(bias), L.ptr(resid), N, L.ptr(out), N, M, N, K,
+                                          epi, variant, L.stream_ptr()), "caco_gemm_f16_wsplit")
+    return out
+
+
+@_on_tensor_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, want_f32: bool = True,
               want_f16: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     _need(x, torch.float32, "x"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
@@ -75,6 +129,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return o32, o16
 
 
+@_on_tensor_device
 def audio_add_pos(x: torch.Tensor, time_inds: torch.Tensor, freq_inds: torch.Tensor, freq_emb: torch.Tensor) -> torch.Tensor:
     """In place: x[m] += sincos(time_inds[m]) + freq_emb[freq_inds[m]] (mae.py:135-142)."""
     _need(x, torch.float32, "x"); _need(time_inds, torch.float32, "time_inds"); _need(freq_inds, torch.float32, "freq_inds")
@@ -86,6 +141,7 @@ def audio_add_pos(x: torch.Tensor, time_inds: torch.Tensor, freq_inds: torch.Ten
     return x
 
 
+@_on_tensor_device
 def attention_audio(qkv: torch.Tensor, mask: torch.Tensor, heads: int) -> torch.Tensor:
     """qkv [B,S,3*D] fp16 (q|k|v), mask [B,S] fp32 (1 = keep) -> [B,S,D] fp16."""
     _need(qkv, torch.float16, "qkv"); _need(mask, torch.float32, "mask")
@@ -97,6 +153,7 @@ def attention_audio(qkv: torch.Tensor, mask: torch.Tensor, heads: int) -> torch.
     return out
 
 
+@_on_tensor_device
 def attention_text(qkv: torch.Tensor, key_mask: torch.Tensor, heads: int) -> torch.Tensor:
     _need(qkv, torch.float16, "qkv"); _need(key_mask, torch.float32, "key_mask")
     B, T, D3 = qkv.shape
@@ -107,6 +164,7 @@ def attention_text(qkv: torch.Tensor, key_mask: torch.Tensor, heads: int) -> tor
     return out
 
 
+@_on_tensor_device
 def text_embed_ln(ids, position_ids, word, pos, type0, gamma, beta, eps: float = 1e-5):
     _need(ids, torch.int64, "ids")
     if position_ids is not None:
@@ -123,6 +181,7 @@ def text_embed_ln(ids, position_ids, word, pos, type0, gamma, beta, eps: float =
     return o32, o16
 
 
+@_on_tensor_device
 def attn_pool(hid, mask, u, c, ln_gamma=None, ln_beta=None, ln_eps: float = 1e-5, want_hidden: bool = False):
     _need(hid, torch.float32, "hid"); _need(mask, torch.float32, "mask"); _need(u, torch.float32, "u"); _need(c, torch.float32, "c")
     B, S, dim = hid.shape
@@ -134,6 +193,7 @@ def attn_pool(hid, mask, u, c, ln_gamma=None, ln_beta=None, ln_eps: float = 1e-5
     return pooled, hid_out
 
 
+@_on_tensor_device
 def sgemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
     _need(a, torch.float32, "a"); _need(w, torch.float32, "w")
     M, K = a.shape
@@ -144,6 +204,7 @@ def sgemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
+@_on_tensor_device
 def l2norm(x: torch.Tensor, eps: float = 1e-10) -> torch.Tensor:
     _need(x, torch.float32, "x")
     out = torch.empty_like(x)
@@ -151,6 +212,7 @@ def l2norm(x: torch.Tensor, eps: float = 1e-10) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def sim_logits(a: torch.Tensor, t: torch.Tensor, logit_scale: torch.Tensor, want_ta: bool = True):
     """(exp(logit_scale)*a) @ t.T and its transpose counterpart (caco.py:208-210)."""
     _need(a, torch.float32, "a"); _need(t, torch.float32, "t"); _need(logit_scale, torch.float32, "logit_scale")
@@ -163,6 +225,7 @@ def sim_logits(a: torch.Tensor, t: torch.Tensor, logit_scale: torch.Tensor, want
     return at, ta
 
 
+@_on_tensor_device
 def frontend(wave: torch.Tensor, max_patches: int, want_log_mel: bool = False, want_f16: bool = False):
     """wave [B, L] fp32 CUDA -> dict(audio_patches [B,P,256], audio_time_inds, audio_freq_inds, audio_mask [B,P])."""
     _need(wave, torch.float32, "wave")
@@ -187,6 +250,7 @@ def frontend(wave: torch.Tensor, max_patches: int, want_log_mel: bool = False, w
     return out
 
 
+@_on_tensor_device
 def frontend_ragged(wave: torch.Tensor, lengths: torch.Tensor, max_patches: int, want_f16: bool = False):
     """Ragged batch: wave [B, stride] fp32 (clip b = wave[b, :lengths[b]]), lengths [B] int32 CUDA -> the same dict as
     `frontend`, every clip treated as eval_caco_torch.py:181-206 treats a single clip of its own length."""
@@ -208,6 +272,7 @@ def frontend_ragged(wave: torch.Tensor, lengths: torch.Tensor, max_patches: int,
     return out
 
 
+@_on_tensor_device
 def topk_rows(x: torch.Tensor, k: int, want_values: bool = False):
     """argsort(-x, dim=-1)[:, :k] (ties: lower column first; NaN last) for x [rows, cols] fp32, k <= 32 -> int32 [rows, k]."""
     _need(x, torch.float32, "x")
@@ -223,6 +288,7 @@ def topk_rows(x: torch.Tensor, k: int, want_values: bool = False):
     return (idx, val) if want_values else idx
 
 
+@_on_tensor_device
 def retrieval_hits(topk: torch.Tensor, key_id: torch.Tensor, gt_id: torch.Tensor, gt_pairs: Optional[torch.Tensor] = None,
                    n_key_ids: int = 0) -> torch.Tensor:
     """Hit bit-mask per query (bit j = rank j+1 is a hit), eval_utils.py:26-41.  gt_pairs None = 'ta' mode."""
@@ -243,6 +309,7 @@ def retrieval_hits(topk: torch.Tensor, key_id: torch.Tensor, gt_id: torch.Tensor
     return out
 
 
+@_on_tensor_device
 def avg_pool_tokens(hid: torch.Tensor, group: int = 8) -> torch.Tensor:
     """[B, S, D] -> [B, S // group, D] mean over groups of `group` consecutive tokens (caco_embeddings.py:124-125)."""
     _need(hid, torch.float32, "hid")

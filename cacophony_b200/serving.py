@@ -5,7 +5,8 @@ a graph removes; at the bench batch (256 pairs) the step is power-bound and a gr
 
 The captured kernels read and write fixed device buffers (tensor maps and pointers are baked into the graph), so requests
 are copied into static input buffers and results are returned as views of static output buffers (valid until the next
-replay).  The reference has no counterpart (it issues one eager model call per clip, eval_caco_torch.py:315-336).
+replay).  The graph shares the model handle's workspaces with eager calls on the same model: replays and eager calls must be
+issued on the same stream (or otherwise ordered), as any two calls on one model must.  The reference has no counterpart (it issues one eager model call per clip, eval_caco_torch.py:315-336).
 """
 from __future__ import annotations
 
@@ -28,16 +29,26 @@ class GraphedPairs:
         self.ids = torch.ones((batch, text_len), dtype=torch.int64, device=dev)
         self.mask = torch.ones((batch, text_len), dtype=torch.float32, device=dev)
         self.ids[:, 0] = 0
+        self._warmup = max(1, warmup)
+        self._capture()
+
+    def _capture(self) -> None:
+        """(Re)capture.  The graph bakes in raw pointers into the model handle's workspaces and packed weights; the handle
+        counts every release of such memory (workspace growth by a larger eager call, re-pack after load_state_dict / .to() /
+        an option change) in ``generation``, and a stale graph is re-captured before it is replayed — never replayed."""
+        dev = self.model._device()
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up off the capture: workspaces, function attributes
-            for _ in range(max(1, warmup)):
+            for _ in range(self._warmup):
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         with torch.cuda.graph(self.graph):
             self.audio_emb, self.text_emb, self.at, self.ta = self._step()
+        self._generation = self.model.generation()
+        self.recaptures = getattr(self, "recaptures", -1) + 1
 
     def _step(self):
         a, t = self.model.encode_pairs(self.wave, self.ids, self.mask, max_patches=self.max_patches)
@@ -50,6 +61,8 @@ class GraphedPairs:
         """(audio -> text logits, text -> audio logits) for one request of the captured shape (views of static buffers)."""
         if tuple(waveform.shape) != tuple(self.wave.shape) or tuple(text_input_ids.shape) != tuple(self.ids.shape):
             raise ValueError(f"GraphedPairs was captured for waveform {tuple(self.wave.shape)} / ids {tuple(self.ids.shape)}")
+        if self.model._packed_key is None or self.model.generation() != self._generation:
+            self._capture()                                 # the handle released memory the old graph points into
         self.wave.copy_(waveform, non_blocking=True)
         self.ids.copy_(text_input_ids, non_blocking=True)
         self.mask.copy_(text_mask, non_blocking=True)

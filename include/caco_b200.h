@@ -63,14 +63,24 @@ int caco_frontend_ragged(const float* wave, const int* lengths, int batch, int s
  * lda/ldw/ldo/ldr are leading dimensions in ELEMENTS.  N % 4 == 0, K % 8 == 0.                       */
 int caco_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ldr,
                   void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream);
-void caco_set_gemm_variant(int variant);
-/* CACO_EPI_BIAS_RESID_F32 with resid == out (in-place residual update): 1 (default) = the add is done by the L2 with
- * red.global.add.v4.f32, 0 = load/add/store in the SM.  Same fp32 result; a measurement switch. */
-void caco_set_gemm_resid_red(int enable);
-/* Programmatic dependent launch of the tower kernels (GEMM, LayerNorm, audio attention): 1 (default) = a kernel's prologue
- * (barrier init, tensor-memory allocation) overlaps its predecessor's tail and it waits with griddepcontrol.wait before
- * touching data; 0 = ordinary stream order.  Same results; a measurement switch. */
-void caco_set_pdl(int enable);
+/* Split-weight form (precision escape hatch): W2 [N, 2K] f16 holds fp16(w) | fp16(w - fp16(w)) per row; the
+ * kernel accumulates A·hi^T + A·lo^T in one pass over a 2K-long reduction (A's k-blocks are re-read), so the weights enter
+ * with ~22 mantissa bits.  Twice the tensor work of caco_gemm_f16. */
+int caco_gemm_f16_wsplit(const void* A, int lda, const void* W2, int ldw, const float* bias, const float* resid, int ldr,
+                         void* out, int ldo, int M, int N, int K, int epi, int variant, void* stream);
+/* f32 [rows, K] -> f16 [rows, 2K] hi | lo (the packing caco_gemm_f16_wsplit reads). */
+int caco_cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K, void* stream);
+/* Execution options.  Every model handle owns a set (caco_model_set_option); op-level calls made outside a handle use the
+ * library defaults changed here.  Names (values): "pdl" (1 = programmatic dependent launch of the tower kernels: a kernel's
+ * prologue overlaps its predecessor's tail, griddepcontrol.wait before touching data), "gemm_variant" (0 = auto, CACO_GEMM_*),
+ * "resid_red" (1 = in-place residual GEMMs add through the L2 with red.global.add.v4.f32, 0 = load/add/store in the SM; same
+ * fp32 result), "attn_poly" (share of the audio attention's exp2 evaluated by an FMA-pipe polynomial: 0 none, 1 = 1/4,
+ * 2 = 1/2, 3 = 3/8), "audio_chunk_rows" / "text_chunk_rows" (token rows per pass of a tower), "split_weights" (0/1: GEMM
+ * weights as fp16 hi + lo, see caco_gemm_f16_wsplit).  Returns 0, or CACO_ERR_ARG for an unknown name / bad value. */
+int caco_set_default_option(const char* name, int value);
+/* fp16 range guard: number of 4-element fp16 stores of GEMM epilogues that had to clamp a value to +-65504 since the last
+ * reset (0 = every operand copy was in range).  Synchronises the device. */
+unsigned int caco_saturation_count(int reset);
 /* live profiling for bench.py: CUDA events around every GEMM launch on its stream.  caco_gemm_profile(1) resets and
  * starts recording; caco_gemm_profile_read synchronises the device and returns the launch count, summed device
  * time (ms) and summed algorithmic FLOPs (2*M*N*K). */
@@ -95,10 +105,6 @@ int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds,
 int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                          void* stream);
 
-/* 0 = default (persistent ping-pong tcgen05 kernel for head_dim 96, = 4), 1 = warp-level mma.sync kernel (head_dim
- * 64 / 96), 2 = one-tile tcgen05 kernel, 3 = persistent tcgen05 kernel with P in shared memory, 4 = ping-pong kernel with P
- * in tensor memory.  1-3 are kept as cross-checks / debugging aids. */
-void caco_set_attention_impl(int impl);
 
 /* ---- K3b: causal text self-attention (roberta.py:86-102, mask from roberta.py:297-310):
  * qkv [batch*T, 3*heads*64] f16, key_mask [batch, T] f32 (1 = keep); allowed(i,j) = j<=i && key_mask[j]. */
@@ -165,7 +171,8 @@ typedef struct {
   int text_heads;    /* 12   */
   int vocab;         /* 50265 */
   int max_pos;       /* 514  */
-  float ln_eps;      /* 1e-5 */
+  float ln_eps;      /* 1e-5  RobertaConfig.layer_norm_eps (roberta.py:22) */
+  float audio_ln_eps; /* 1e-5 nn.LayerNorm default of the audio tower (mae.py:68,76,123); <= 0 means 1e-5 */
 } caco_config;
 
 int caco_model_create(const caco_config* cfg, caco_model** out);
@@ -176,6 +183,12 @@ void caco_model_destroy(caco_model* m);
  * (biases, LayerNorm params, embeddings are used in place).  Unknown keys ("decoder_module.*") -> 1. */
 int caco_model_set_tensor(caco_model* m, const char* key, const float* dev_ptr, int64_t numel);
 int caco_model_pack(caco_model* m, void* stream);
+/* Per-handle execution option (names as in caco_set_default_option; a new handle starts from the library defaults).
+ * "split_weights" takes effect at the next call (the handle re-packs its weight arena from the registered tensors). */
+int caco_model_set_option(caco_model* m, const char* name, int value);
+/* Counter bumped whenever the handle releases device memory a previously enqueued or captured call may reference (workspace
+ * growth, re-pack, move to another device): a CUDA graph captured from this handle is stale once it changes. */
+uint64_t caco_model_generation(const caco_model* m);
 
 /* CACO.get_audio_embedding (caco.py:123-150).  hidden_out [batch, seq, hidden] f32 or NULL. */
 int caco_model_audio_embedding(caco_model* m, const float* patches, const float* time_inds, const float* freq_inds,

@@ -1,6 +1,7 @@
 """A/B timing of the full bench step under library switches, interleaved in ONE process on ONE box (box-to-box and
 run-to-run spread is ~3 %, larger than most single-kernel effects).
-Usage: python scripts/ab_step.py name=setter:value[,setter:value] ...   e.g.  red=caco_set_gemm_resid_red:1 nored=caco_set_gemm_resid_red:0"""
+Usage: python scripts/ab_step.py name=option:value[,option:value] ...   e.g.  red=resid_red:1 nored=resid_red:0
+(options: the per-model execution options of include/caco_b200.h, set with model.set_option)"""
 import json
 import sys
 
@@ -31,8 +32,8 @@ def step():
 res = {n: [] for n, _ in arms}
 for rnd in range(4):
     for name, sets in arms:
-        for fn, v in sets:
-            getattr(lib, fn)(v)
+        for opt, v in sets:
+            model.set_option(opt, v)
         for _ in range(3):
             step()
         torch.cuda.synchronize()

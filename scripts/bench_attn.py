@@ -1,4 +1,4 @@
-"""Micro-benchmark of the audio attention kernels (tcgen05 vs warp-level mma.sync) at the bench shape."""
+"""Micro-benchmark of the audio attention kernel at the bench shape for every exp2 split (attn_poly 0..3)."""
 import json
 import sys
 
@@ -14,23 +14,22 @@ mask = torch.ones(B, S, device="cuda")
 mask[:, 496:] = 0
 lib = L.load()
 res = {}
-for impl, name in ((4, "tcgen05_pingpong"), (3, "tcgen05_persistent"), (2, "tcgen05"), (1, "mma_sync")):
-    lib.caco_set_attention_impl(impl)
-    for _ in range(3):
-        o = ops.attention_audio(qkv, mask, H)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        o = ops.attention_audio(qkv, mask, H)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    fl = 4.0 * B * H * S * S * dh
-    res[name] = o.float()
-    print(json.dumps({"impl": name, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
-d = (res["tcgen05"] - res["mma_sync"]).abs().max().item()
-d2 = (res["tcgen05_persistent"] - res["mma_sync"]).abs().max().item()
-d3 = (res["tcgen05_pingpong"] - res["mma_sync"]).abs().max().item()
-print(json.dumps({"max_abs_diff_between_impls": d, "persistent_vs_mma_sync": d2, "pingpong_vs_mma_sync": d3}))
-lib.caco_set_attention_impl(0)
+for rnd in range(2):
+    for poly, name in ((0, "mufu_only"), (1, "poly_1_of_4"), (3, "poly_3_of_8"), (2, "poly_1_of_2")):
+        lib.caco_set_default_option(b"attn_poly", poly)
+        for _ in range(3):
+            o = ops.attention_audio(qkv, mask, H)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            o = ops.attention_audio(qkv, mask, H)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        fl = 4.0 * B * H * S * S * dh
+        res[name] = o.float()
+        print(json.dumps({"round": rnd, "impl": name, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+ref = res["mufu_only"]
+print(json.dumps({k: float((v - ref).abs().max()) for k, v in res.items()}))
+lib.caco_set_default_option(b"attn_poly", 0)

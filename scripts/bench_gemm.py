@@ -29,7 +29,7 @@ VARIANTS = {"cg1_n256": L.GEMM_CG1_N256, "cg1_n128": L.GEMM_CG1_N128, "cg2_n256"
 def main():
     names = [a for a in sys.argv[1:] if a in VARIANTS] or list(VARIANTS)
     if "nored" in sys.argv[1:]:
-        L.load().caco_set_gemm_resid_red(0)
+        L.load().caco_set_default_option(b"resid_red", 0)
     for vn in names:
         v = VARIANTS[vn]
         for name, M, N, K, epi in SHAPES:

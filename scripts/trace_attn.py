@@ -13,7 +13,6 @@ qkv = torch.randn(B, S, 3 * H * dh, device="cuda").half()
 mask = torch.ones(B, S, device="cuda")
 mask[:, 496:] = 0
 lib = L.load()
-lib.caco_set_attention_impl(4)
 trace_fn = lib.caco_attn3_trace
 trace_fn.argtypes = [C.c_void_p]
 for _ in range(2):

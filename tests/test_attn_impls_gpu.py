@@ -1,5 +1,6 @@
-"""GPU: every audio-attention implementation (persistent ping-pong tcgen05, persistent, one-tile tcgen05, mma.sync) against
-the same fp32 reference math, including ragged masks and the sharp-softmax (rescale) path."""
+"""GPU: the audio-attention kernel in every exp2 split it ships (attn_poly 0..3: none, 1/4, 1/2, 3/8 of the scores through the
+FMA-pipe polynomial instead of MUFU.EX2) against the same fp32 reference math, including ragged masks, holes in the mask,
+one live key, and the sharp-softmax (lazy rescale) path."""
 import math
 
 import numpy as np
@@ -12,20 +13,21 @@ from cacophony_b200 import _lib as L
 from cacophony_b200 import ops
 from tests.test_ops_gpu import _attn_ref
 
-IMPLS = {"mma_sync": 1, "tc_one_tile": 2, "tc_persistent": 3, "tc_pingpong": 4}
+IMPLS = {"mufu_only": 0, "poly_1_of_4": 1, "poly_1_of_2": 2, "poly_3_of_8": 3}
+DEFAULT_POLY = 0
 
 
 @pytest.fixture(autouse=True)
 def _restore_impl():
     yield
-    L.load().caco_set_attention_impl(0)
+    assert L.load().caco_set_default_option(b"attn_poly", DEFAULT_POLY) == 0
 
 
 @pytest.mark.parametrize("impl", list(IMPLS))
 @pytest.mark.parametrize("S,valid,sharp", [(500, 496, 1.0), (500, 248, 1.0), (77, 32, 1.0), (129, 129, 1.0), (500, 496, 4.0),
                                            (1500, 1500, 1.0), (300, 1, 1.0)])
 def test_attention_impl(impl, S, valid, sharp):
-    L.load().caco_set_attention_impl(IMPLS[impl])
+    assert L.load().caco_set_default_option(b"attn_poly", IMPLS[impl]) == 0
     g = torch.Generator().manual_seed(S + valid)
     B, H, dh = 3, 8, 96
     qkv = torch.randn(B, S, 3 * H * dh, generator=g) * 1.2
