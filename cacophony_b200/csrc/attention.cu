@@ -242,8 +242,8 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
   }
 }
 
-int attention_audio_tc3(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
-                        cudaStream_t stream);
+int attention_audio_pp(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
+                       cudaStream_t stream);
 
 int attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                     cudaStream_t stream) {
@@ -251,7 +251,7 @@ int attention_audio(const void* qkv, const float* mask, void* out, int batch, in
   // head_dim 96 (the checkpoint's audio tower): the persistent ping-pong tcgen05 kernel, up to 4096 keys (its per-item key
   // bias lives in shared memory); anything else (head_dim 64 configurations, longer sequences) takes the warp-level
   // flash kernel below.
-  if (dh == 96 && seq <= 4096) return attention_audio_tc3(qkv, mask, out, batch, seq, heads, dh, stream);
+  if (dh == 96 && seq <= 4096) return attention_audio_pp(qkv, mask, out, batch, seq, heads, dh, stream);
   if ((heads * dh) % 8) return CACO_ERR_ARG;
   const float scale_log2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   dim3 grid((seq + AT_BM - 1) / AT_BM, heads, batch);

@@ -39,7 +39,6 @@ struct Options {
   int pdl = 1;              // programmatic dependent launch of the tower kernels (ptx.cuh: pdl_wait / pdl_launch)
   int gemm_variant = 0;     // 0 = auto, else CACO_GEMM_*
   int resid_red = 1;        // in-place residual GEMMs add through the L2 (red.global.add.v4.f32)
-  int attn_poly = 0;        // audio attention: share of the exp2 evaluated on the FMA pipe (0 none, 1 = 1/4, 2 = 1/2, 3 = 3/8)
   int audio_chunk_rows = 131072;   // token rows per pass of the audio tower (larger batches are chunked)
   int text_chunk_rows = 131072;
   int split_weights = 0;    // precision mode: GEMM weights as fp16 hi + lo (two accumulating MMA passes)

@@ -388,7 +388,6 @@ int set_option(Options& o, const char* name, int value) {
   if (n == "pdl") o.pdl = value != 0;
   else if (n == "gemm_variant") { if (value < 0 || value > CACO_GEMM_CG2_N256_E16) return CACO_ERR_ARG; o.gemm_variant = value; }
   else if (n == "resid_red") o.resid_red = value != 0;
-  else if (n == "attn_poly") { if (value < 0 || value > 3) return CACO_ERR_ARG; o.attn_poly = value; }
   else if (n == "audio_chunk_rows") { if (value < 1) return CACO_ERR_ARG; o.audio_chunk_rows = value; }
   else if (n == "text_chunk_rows") { if (value < 1) return CACO_ERR_ARG; o.text_chunk_rows = value; }
   else if (n == "split_weights") o.split_weights = value != 0;

@@ -300,7 +300,7 @@ class CACO(nn.Module):
     # ---- execution options (per model; see caco_set_default_option in include/caco_b200.h for the names) -------------
     def set_option(self, name: str, value: int) -> None:
         """E.g. ``set_option("split_weights", 1)``: GEMM weights as fp16 hi + lo (two accumulating tensor-core passes, the
-        precision escape hatch of SURVEY.md 7.3), ``"audio_chunk_rows"``, ``"attn_poly"``, ``"pdl"``."""
+        precision escape hatch of SURVEY.md 7.3), ``"audio_chunk_rows"``, ``"pdl"``."""
         self._options[name] = int(value)
         if self._handle is not None:
             L.check(L.load().caco_model_set_option(self._handle, name.encode(), int(value)), f"caco_model_set_option({name})")

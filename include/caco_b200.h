@@ -74,8 +74,7 @@ int caco_cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K
  * library defaults changed here.  Names (values): "pdl" (1 = programmatic dependent launch of the tower kernels: a kernel's
  * prologue overlaps its predecessor's tail, griddepcontrol.wait before touching data), "gemm_variant" (0 = auto, CACO_GEMM_*),
  * "resid_red" (1 = in-place residual GEMMs add through the L2 with red.global.add.v4.f32, 0 = load/add/store in the SM; same
- * fp32 result), "attn_poly" (share of the audio attention's exp2 evaluated by an FMA-pipe polynomial: 0 none, 1 = 1/4,
- * 2 = 1/2, 3 = 3/8), "audio_chunk_rows" / "text_chunk_rows" (token rows per pass of a tower), "split_weights" (0/1: GEMM
+ * fp32 result), "audio_chunk_rows" / "text_chunk_rows" (token rows per pass of a tower), "split_weights" (0/1: GEMM
  * weights as fp16 hi + lo, see caco_gemm_f16_wsplit).  Returns 0, or CACO_ERR_ARG for an unknown name / bad value. */
 int caco_set_default_option(const char* name, int value);
 /* fp16 range guard: number of 4-element fp16 stores of GEMM epilogues that had to clamp a value to +-65504 since the last
@@ -101,7 +100,8 @@ int caco_audio_add_pos(float* x, const float* time_inds, const float* freq_inds,
 
 /* ---- K3a: audio self-attention, nn.MultiheadAttention semantics (mae.py:69-74,89-92):
  * qkv [batch*seq, 3*heads*dh] f16 (q|k|v packed in-proj output), q scaled by 1/sqrt(dh) inside,
- * keys with mask==0 get -inf, softmax in fp32, out [batch*seq, heads*dh] f16.  dh in {64, 96}.            */
+ * keys with mask==0 get -inf, softmax in fp32, out [batch*seq, heads*dh] f16.  dh = 96 (seq <= 4096): the persistent
+ * ping-pong tcgen05 kernel (attention_pp.cu); dh = 64, or longer sequences: the warp-level flash kernel (attention.cu). */
 int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                          void* stream);
 

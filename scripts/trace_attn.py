@@ -13,7 +13,7 @@ qkv = torch.randn(B, S, 3 * H * dh, device="cuda").half()
 mask = torch.ones(B, S, device="cuda")
 mask[:, 496:] = 0
 lib = L.load()
-trace_fn = lib.caco_attn3_trace
+trace_fn = lib.caco_attn_trace
 trace_fn.argtypes = [C.c_void_p]
 for _ in range(2):
     ops.attention_audio(qkv, mask, H)
@@ -24,8 +24,8 @@ torch.cuda.synchronize()
 trace_fn(None)
 t = buf.cpu().view(2, 64, 8)
 t0 = int(t[t > 0].min())
-names = [["iter", "inputs", "pA_seen", "pvA+qkA", "pB_seen", "pvB+qkB", "-", "-"],
-         ["wait_s", "s_ready", "max_done", "p_written", "pv_done", "stored", "-", "-"]]
+names = [["iter", "waited", "A_issued", "pB_seen", "B_issued", "-", "-", "-"],
+         ["wait_s", "s_ready", "s_loaded", "max_done", "p_written", "pv_done", "stored", "-"]]
 for role, rn in ((0, "MMA"), (1, "SMX")):
     print(rn, " ".join(f"{n:>10s}" for n in names[role]))
     for g in range(14):
