@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the Cacophony inference hot path on B200 (driver contract: see the task prompt).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--workload pairs|zeroshot]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic input: B = 256 audio-text pairs per GPU
@@ -14,8 +14,12 @@ exp(logit_scale)-scaled cosine-similarity matrix — BASELINE.json configs[2] (c
                D2H of the logits block are inside the timed region (double-buffered so copies overlap compute)
   roofline     the dominant kernel family (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time measured live in the timed
                region, against the MEASURED sustained bf16 GEMM peak (MEASURED_PEAKS.json)
-  cpu_baseline the CPU port of the reference algorithm (oracle/) timed on this box's host cores on a bounded sample
-  --impl reference   times that CPU implementation alone (the reference arm for this tier)
+  cpu_baseline the UNMODIFIED reference (oracle/_ref archive, kind "reference"; the oracle port only if the archive is
+               missing, kind "port") timed on this box's host cores on a bounded sample
+  gpu_library_baseline   the same unmodified reference model moved to this GPU (torch's cuBLAS / native-MHA kernels, the bar
+               SURVEY.md 2 names: eval_caco_torch.py:549 --device cuda): fp32 without TF32, TF32, fp16 autocast; pairs/s at B
+  --impl reference   times the reference's own CPU implementation alone (the reference arm for this tier)
+  --workload zeroshot    BASELINE config 5 (400 x 5 s clips, 50 prompts of 100 tokens) as a first-class workload: clips/s
 """
 from __future__ import annotations
 
@@ -52,9 +56,11 @@ def gemm_traffic_from_profile():
     GEMMs of one audio layer — QKV, out-proj, fc1, fc2 — dram__bytes_read.sum + dram__bytes_write.sum), averaged per
     launch.  Static evidence read from the repo, not measured in this run (ncu cannot run inside a timed bench)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")
-    if not os.path.exists(p):
-        return None, None
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")))
+    if not cands:
+        return None, None, None
+    p = cands[-1]                                  # the latest round's capture
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, n = 0.0, 0
     with open(p, newline="") as f:
@@ -65,7 +71,7 @@ def gemm_traffic_from_profile():
                 if k.startswith(("dram__bytes_read.sum", "dram__bytes_write.sum")) and v:
                     tot += float(v) * unit.get(k.split("[")[1].rstrip("]"), 1.0)
             n += 1
-    return (tot / n, n) if n else (None, None)
+    return (tot / n, n, os.path.relpath(p, ROOT)) if n else (None, None, None)
 
 
 def workload_config(batch: int, world: int):
@@ -123,28 +129,113 @@ def synth_inputs(batch: int, seed: int):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores (checker code used as a timed baseline)
 # ----------------------------------------------------------------------------------------------------------------
+def _reference_or_none():
+    """(create_caco_model, eval module) of the unmodified reference from oracle/_ref, or None (then the port is timed)."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.load()
+    except Exception as e:                    # archive missing on this box
+        sys.stderr.write(f"bench.py: reference archive unavailable ({e}); timing the oracle port instead\n")
+        return None
+
+
 def cpu_pairs_per_s(sd_cpu, sample_pairs: int, steps: int, warmup: int, budget_s: float = 0.0):
-    """Times `steps` passes of `sample_pairs` pairs (after `warmup` untimed passes) through the CPU port of the reference
-    algorithm with every host thread.  budget_s > 0: `steps` is a minimum and passes continue until about budget_s seconds
-    of timed CPU work have been done (bench.py's cpu_baseline leg: ~10-30 s).  Returns (pairs/s, s per pass, passes)."""
+    """Times `steps` passes of `sample_pairs` pairs (after `warmup` untimed passes) through the reference's own CPU
+    implementation with every host thread: its frontend one clip at a time (eval_caco_torch.py:181-206, as its drivers call
+    it) and ONE batched CACO.forward (caco.py:242-261).  budget_s > 0: `steps` is a minimum and passes continue until about
+    budget_s seconds of timed CPU work have been done (bench.py's cpu_baseline leg: ~10-30 s).
+    Returns (pairs/s, s per pass, passes, kind)."""
     import torch
-    from oracle import caco_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     wave, ids, mask = synth_inputs(sample_pairs, 99)
+    ref = _reference_or_none()
+    if ref is not None:
+        create_ref, E = ref
+        model = create_ref().eval()
+        missing, unexpected = model.load_state_dict(sd_cpu, strict=False)
+        assert not unexpected and all(k.startswith("decoder_module") for k in missing)
+        cfg = E.DatasetConfig(patches_seq_len=MAX_PATCHES)
+
+        def one_pass():
+            bs = [E.prepare_audio_batch(wave[i:i + 1], cfg, "cpu") for i in range(sample_pairs)]
+            ab = {k: torch.cat([b[k] for b in bs]) for k in bs[0]}
+            return model(**ab, text_input_ids=ids, text_mask=mask.long())
+        kind = "reference"
+    else:
+        from oracle import caco_oracle as O
+
+        def one_pass():
+            ab = O.prepare_audio_batch(list(wave.numpy()), MAX_PATCHES)
+            return O.forward(sd_cpu, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"], ids, mask)
+        kind = "port"
     times = []
     with torch.no_grad():
         i = 0
         while True:
             t0 = time.perf_counter()
-            ab = O.prepare_audio_batch(list(wave.numpy()), MAX_PATCHES)
-            O.forward(sd_cpu, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"], ids, mask)
+            one_pass()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
             i += 1
             if len(times) >= steps and (budget_s <= 0 or sum(times) >= budget_s or len(times) >= 40):
                 break
     dt = sum(times) / len(times)
-    return sample_pairs / dt, dt, len(times)
+    return sample_pairs / dt, dt, len(times), kind
+
+
+def gpu_library_baseline(sd_cpu, batch_d, ids_d, mask_d, dev, steps: int = 5):
+    """The unmodified reference model on THIS GPU through torch's own kernels (cuBLAS GEMMs, the native multi-head-attention
+    fast path, eager LayerNorm / GELU): model.to(device) as eval_caco_torch.py:549 --device cuda would run it, CACO.forward on
+    the same B pairs (patches already on the device: the frontend is outside this number, which favours the reference).
+    Three settings: fp32 with TF32 off (the reference's numerics), TF32 on, fp16 autocast.  Returns a dict or None."""
+    import torch
+    ref = _reference_or_none()
+    if ref is None:
+        return None
+    create_ref, _ = ref
+    out = {"unit": UNIT, "batch": int(ids_d.shape[0]), "what": "unmodified reference CACO.forward on this GPU, torch "
+           + torch.__version__ + " library kernels, device-resident patches, CUDA events"}
+    try:
+        model = create_ref().eval()
+        model.load_state_dict(sd_cpu, strict=False)
+        model = model.to(dev)
+        args = dict(batch_d, text_input_ids=ids_d, text_mask=mask_d.long())
+        B = int(ids_d.shape[0])
+
+        def timed(fn):
+            with torch.no_grad():
+                for _ in range(2):
+                    r = fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    r = fn()
+                e1.record()
+                torch.cuda.synchronize()
+            return B * steps / (e0.elapsed_time(e1) / 1e3), r
+        prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        out["fp32"], r32 = timed(lambda: model(**args))
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        out["tf32"], _ = timed(lambda: model(**args))
+
+        def autocast():
+            with torch.autocast("cuda", dtype=torch.float16):
+                return model(**args)
+        out["fp16_autocast"], _ = timed(autocast)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        for k in ("fp32", "tf32", "fp16_autocast"):
+            out[k] = round(out[k], 1)
+        out["_logits_fp32"] = r32[0]
+        del model
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:                    # never fail the bench because of the comparison leg
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+        return out
 
 
 def cpu_model():
@@ -164,14 +255,17 @@ def run_reference(args):
     torch.manual_seed(0)
     sd = {k: v for k, v in cb.create_caco_model().state_dict().items()}
     sample = 16
-    value, dt, _ = cpu_pairs_per_s(sd, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
+    value, dt, _, kind = cpu_pairs_per_s(sd, sample, steps, warm)
     cores = os.cpu_count() or 1
-    desc = f"{sample} pairs per step (same clip/caption shape as the GPU arm), fp32 torch CPU ops, {cores} threads"
+    what = ("the unmodified reference (src/caco_torch + src/eval/eval_caco_torch.py from oracle/_ref): its frontend per clip, "
+            "one batched CACO.forward") if kind == "reference" else "the oracle port of the reference algorithm"
+    desc = f"{sample} pairs per step (same clip/caption shape as the GPU arm), {what}, fp32 torch CPU ops, {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 1)), "ms_per_step": round(dt * 1e3, 2),
+            "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args.batch, max(1, args.gpus)), sample=desc),
-            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
                              "cpu": cpu_model()},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -214,10 +308,12 @@ def run_ours(args):
         if args.serial_towers or serial:
             a = model.encode_audio(w, max_patches=MAX_PATCHES)
             t = model.encode_text(i, m)
-        else:
-            a, t = model.encode_pairs(w, i, m, max_patches=MAX_PATCHES)
-        if world > 1:
-            return cdist.sharded_contrastive_logits(model, a, t)
+            if world > 1:
+                return cdist.sharded_contrastive_logits(model, a, t)
+            return model.similarity(a, t)
+        if world > 1:           # text embeddings gathered under the audio tower, audio embeddings after it
+            return cdist.sharded_pairs_logits(model, w, i, m, max_patches=MAX_PATCHES)
+        a, t = model.encode_pairs(w, i, m, max_patches=MAX_PATCHES)
         return model.similarity(a, t)
 
     def barrier():
@@ -298,23 +394,50 @@ def run_ours(args):
     ms_e2e = s0.elapsed_time(s1)
     checksum = float(out_h[(args.steps - 1) & 1].double().sum())       # the host really reads the result
 
+    # ---- what follows the towers (N > 1: all-gather of the audio embeddings + the two row-block similarity launches; N = 1:
+    # the similarity kernel), timed alone on fixed embeddings: names the un-overlappable tail of the step
+    a_fix = torch.nn.functional.normalize(torch.randn(B, 768, device=dev), dim=-1)
+    t_fix = torch.nn.functional.normalize(torch.randn(B, 768, device=dev), dim=-1)
+
+    def tail():
+        if world > 1:
+            t_all = cdist.gather_embedding(t_fix, None, "text")
+            at_b, _ = model.similarity(a_fix, t_all, want_ta=False)
+            a_all = cdist.gather_embedding(a_fix, None, "audio")
+            return at_b, model.similarity(t_fix, a_all, want_ta=False)[0]
+        return model.similarity(a_fix, t_fix)
+    for _ in range(3):
+        tail()
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(20):
+        tail()
+    q1.record()
+    barrier()
+    tail_ms = q0.elapsed_time(q1) / 20
+
     # ---- max over ranks ------------------------------------------------------------------------------------------
-    t = torch.tensor([ms_total, ms_e2e, g_ms.value, ms_serial], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, g_ms.value, ms_serial, tail_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [round(float(x[0]) / args.steps, 3) for x in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, gemm_ms, ms_serial = [float(x) for x in t.cpu()]
+    ms_total, ms_e2e, gemm_ms, ms_serial, tail_ms = [float(x) for x in t.cpu()]
     pairs = B * world * args.steps
     value = pairs / (ms_total / 1e3)
     e2e_value = pairs / (ms_e2e / 1e3)
     peaks = _peaks()
     achieved = g_fl.value / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-    traffic, traffic_n = gemm_traffic_from_profile()
+    traffic, traffic_n, traffic_src = gemm_traffic_from_profile()
     roof = {"bound": "tensor", "kernel": "gemm_f16_kernel (tcgen05.mma kind::f16, fp16 operands, fp32 accumulate)",
             "achieved": round(achieved, 1) if achieved else None, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": round(achieved / peaks["bf16_sustained"], 4) if achieved else None,
             "traffic": round(traffic) if traffic else None,
             "traffic_note": (f"DRAM bytes per launch, mean of the {traffic_n} audio-layer GEMMs (QKV, out-proj, fc1, fc2) in "
-                             "profiles/r01_ncu_full_summary.csv; algorithmic bytes of the same four: 1081e6 per launch") if traffic else None,
+                             f"{traffic_src}; algorithmic bytes of the same four: 1081e6 per launch") if traffic else None,
             "peak_source": f"{peaks['src']} sustained bf16 GEMM (burst {peaks['bf16_burst']})",
             "launches_per_step": n_gemm // max(1, args.steps), "share_of_step": round(gemm_ms / ms_serial, 4),
             "timed_on": f"serial-stream replay of the same {args.steps} steps ({ms_serial / args.steps:.2f} ms/step), right after the main region",
@@ -340,16 +463,28 @@ def run_ours(args):
                 "achieved": round(ln_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ln_gbs / peaks["hbm"], 4),
                 "bytes_per_launch": ln_bytes, "us_per_launch": round(ln_ms * 1e3, 2),
                 "timed_on": "20 back-to-back launches on a 393 MB input (> L2), CUDA events",
-                "traffic_note": "ncu: 0.393 GB read + 0.168 GB written per launch (profiles/r01_ncu_full_summary.csv)"}
+                "traffic_note": "ncu: 0.393 GB read + 0.168 GB written per launch (profiles/r01_ncu_full_summary.csv; kernel unchanged)"}
     del xr
 
-    cpu = None
+    cpu, lib_base = None, None
     if sd_cpu is not None:
-        v, dt, n_pass = cpu_pairs_per_s(sd_cpu, 16, 2, 1, budget_s=12.0)
+        # the unmodified reference on THIS GPU through torch's library kernels, on the same inputs
+        ab = cb.prepare_audio_batch(wave_d, cb.DatasetConfig(patches_seq_len=MAX_PATCHES), dev)
+        lib_base = gpu_library_baseline(sd_cpu, ab, ids_d, mask_d, dev) if not args.no_lib else None
+        if lib_base is not None and "_logits_fp32" in lib_base:
+            ref_logits = lib_base.pop("_logits_fp32")
+            ours = step(wave_d, ids_d, mask_d)[0]
+            lib_base["max_abs_dlogit_vs_ours"] = round(float((ours - ref_logits).abs().max()), 6)
+            lib_base["speedup_e2e_over"] = {k: round(e2e_value / lib_base[k], 2) for k in ("fp32", "tf32", "fp16_autocast")
+                                            if lib_base.get(k)}
+            del ref_logits
+        del ab
+        v, dt, n_pass, kind = cpu_pairs_per_s(sd_cpu, 16, 2, 1, budget_s=12.0)
         cores = os.cpu_count() or 1
-        cpu = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model(),
+        cpu = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model(),
                "sample": f"16 pairs per pass, 1 warm-up + {n_pass} timed passes ({dt:.2f} s each, {dt * n_pass:.0f} s of CPU work), "
-                         f"fp32 torch CPU ops, {cores} threads"}
+                         + ("unmodified reference (oracle/_ref): frontend per clip + one batched CACO.forward, " if kind == "reference"
+                            else "oracle port, ") + f"fp32 torch CPU ops, {cores} threads"}
 
     if rank == 0:
         h2d = wave_h.numel() * 4 + ids_h.numel() * 8 + mask_h.numel() * 4
@@ -361,7 +496,147 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": round(ms_e2e / args.steps, 3), "checksum": checksum},
-                "gpu_launches": int(launches), "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
+                "gpu_library_baseline": lib_base,
+                "tail": {"ms": round(tail_ms, 4), "what": ("text gather + audio gather (NCCL all_gather_into_tensor, 0.79 MB per "
+                         "rank each) + two [B, N*B] similarity launches, timed alone; in the step the text gather is hidden under "
+                         "the audio tower") if world > 1 else "similarity kernel (both directions), timed alone"},
+                "per_rank_ms_per_step": per_rank}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: zero-shot classification, ESC-50 shape: 400 clips of 80 000 samples (5 s), 50 prompts
+# padded to 100 tokens with 8-12 valid ones; clips sharded across ranks, prompts encoded by every rank, top-1 on the device
+# ----------------------------------------------------------------------------------------------------------------
+def run_zeroshot(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cacophony_b200 as cb
+    from cacophony_b200 import _lib as L
+    from cacophony_b200 import dist as cdist
+    from cacophony_b200 import eval as ev
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    N_CLIPS, N_CLASSES, CLIP, T = 400, 50, 80000, 100
+    torch.manual_seed(0)
+    model = cb.create_caco_model()
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(4321)
+    waves_h = (0.1 * (2.0 * torch.rand(N_CLIPS, CLIP, generator=g) - 1.0)).float().pin_memory()
+    ids_h = torch.full((N_CLASSES, T), 1, dtype=torch.int64)
+    mask_h = torch.zeros(N_CLASSES, T, dtype=torch.float32)
+    for c in range(N_CLASSES):
+        n = int(torch.randint(8, 13, (1,), generator=g))
+        ids_h[c, :n] = torch.randint(3, 50265, (n,), generator=g)
+        ids_h[c, 0], ids_h[c, n - 1] = 0, 2
+        mask_h[c, :n] = 1
+    ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
+    lo, hi = cdist.shard_range(N_CLIPS, rank, world)
+    lens = torch.full((hi - lo,), CLIP, dtype=torch.int32, device=dev)
+    cfg = cb.DatasetConfig(patches_seq_len=MAX_PATCHES)
+
+    # trimmed shapes from HOST knowledge (clip length, prompt lengths): no device read-back inside a step
+    p_trim = max(8, min(cfg.patches_seq_len, (((CLIP + 159) // 160) // 16) * 8))
+    t_trim = min(T, -(-int(mask_h.sum(1).max()) // 8) * 8)
+
+    def step(w_dev, ids_dev, mask_dev, trim):
+        """class embeddings (every rank), this rank's clips, logits + top-1 on the device, predictions gathered."""
+        if trim:
+            t = model.encode_text(ids_dev[:, :t_trim].contiguous(), mask_dev[:, :t_trim].contiguous())
+            a = model.encode_audio(w_dev, max_patches=p_trim, lengths=lens)
+        else:
+            t = model.encode_text(ids_dev, mask_dev)
+            a = model.encode_audio(w_dev, max_patches=cfg.patches_seq_len, lengths=lens)
+        top = ev.zero_shot_topk(model, a, t, 1)
+        return cdist.gather_rows(top, N_CLIPS) if world > 1 else top
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    w_d, ids_d, mask_d = waves_h[lo:hi].to(dev), ids_h.to(dev), mask_h.to(dev)
+    res = {}
+    launches = 0
+    for trim in (False, True):
+        for _ in range(max(args.warmup, 3)):
+            top = step(w_d, ids_d, mask_d, trim)
+        barrier()
+        l0 = lib.caco_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            top = step(w_d, ids_d, mask_d, trim)
+        e1.record()
+        barrier()
+        if not trim:
+            launches = lib.caco_launch_count() - l0
+        # end to end: pinned host waveforms / ids -> device inside the timed region, predictions read back
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            wd = waves_h[lo:hi].to(dev, non_blocking=True)
+            top_h = step(wd, ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True), trim).cpu()
+        s1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1), s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[trim] = (float(t[0]) / args.steps, float(t[1]) / args.steps, top_h)
+    agree = None
+    if rank == 0:
+        # top-1 agreement with the CPU oracle on a 16-clip sample (the oracle takes ~0.3 s per clip)
+        from oracle import caco_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        sample = list(range(0, N_CLIPS, N_CLIPS // 16))[:16]
+        with torch.no_grad():
+            ab = O.prepare_audio_batch([waves_h[i].numpy() for i in sample], MAX_PATCHES)
+            a_ref, _ = O.get_audio_embedding(sd_cpu, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"],
+                                             ab["audio_mask"], normalize=True)
+            t_ref, _ = O.get_text_embedding(sd_cpu, ids_h, mask_h, normalize=True)
+            logits = float(np.exp(sd_cpu["logit_scale"].item())) * a_ref @ t_ref.T
+        ref_top = logits.argmax(-1)
+        srt = logits.sort(-1).values
+        clear = (srt[:, -1] - srt[:, -2]) > 2e-2            # ties aside (SURVEY.md 8d)
+        ours = res[False][2][sample, 0].long()
+        ours_trim = res[True][2][sample, 0].long()
+        agree = {"sample_clips": len(sample), "clear_margin": int(clear.sum()),
+                 "top1_equal_untrimmed": int((ours[clear] == ref_top[clear]).sum()),
+                 "top1_equal_trimmed": int((ours_trim[clear] == ref_top[clear]).sum()),
+                 "trimmed_equals_untrimmed_all_400": bool(torch.equal(res[False][2], res[True][2]))}
+    if rank == 0:
+        ms, ms_e2e, _ = res[False]
+        ms_t, ms_e2e_t, _ = res[True]
+        line = {"metric": "zero-shot classification clips/sec (ESC-50 shape: 400 x 5 s clips, 50 prompts)", "unit": "clips/s",
+                "value": round(N_CLIPS / (ms / 1e3), 1), "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate+residual", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: 400 clips x 80000 samples (248 valid of 500 token slots, all 500 computed "
+                                       "as the reference does), 50 prompts padded to 100 tokens (8-12 valid), class embeddings "
+                                       "recomputed every step on every rank, logits + top-1 on the device",
+                           "clips_per_gpu": hi - lo, "parallelism": f"dp{world}"},
+                "trim_padding": {"value": round(N_CLIPS / (ms_t / 1e3), 1), "ms_per_step": round(ms_t, 3),
+                                 "what": "tower run on the 248 valid token slots / 16 prompt columns only; same predictions"},
+                "e2e": {"value": round(N_CLIPS / (ms_e2e / 1e3), 1), "unit": "clips/s", "ms_per_step": round(ms_e2e, 3),
+                        "h2d_bytes_per_step": (hi - lo) * CLIP * 4 + N_CLASSES * T * 12, "d2h_bytes_per_step": N_CLIPS * 4,
+                        "trim_padding_value": round(N_CLIPS / (ms_e2e_t / 1e3), 1)},
+                "gpu_launches": int(launches), "oracle_agreement": agree}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -374,12 +649,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_library_baseline legs")
+    ap.add_argument("--no-lib", action="store_true", help="skip the gpu_library_baseline leg")
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "zeroshot"],
+                    help="pairs = BASELINE configs 3/4 (headline); zeroshot = config 5 (400 x 5 s clips, 50 prompts of 100 tokens)")
     ap.add_argument("--serial-towers", action="store_true", help="run the text tower after the audio tower on one stream")
     ap.add_argument("--profile", action="store_true", help="profiling run: resident-input region only (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "zeroshot":
+        run_zeroshot(args)
     else:
         run_ours(args)
 

@@ -105,15 +105,48 @@ def embed_text_ids(model: CACO, ids: torch.Tensor, mask: torch.Tensor, batch_siz
 @torch.no_grad()
 def embed_waveforms(model: CACO, waves: Sequence[Any], datasetconfig: Optional[DatasetConfig] = None, batch_size: int = 256,
                     trim_padding: bool = True) -> torch.Tensor:
-    """L2-normalised audio embeddings of a list of (ragged) 16 kHz clips: pinned ragged packing -> async H2D -> ragged frontend
-    + audio tower, `batch_size` clips per library call."""
+    """L2-normalised audio embeddings of a list of (ragged) 16 kHz clips, `batch_size` clips per library call.  Host clips
+    (numpy / CPU tensors): pinned ragged packing -> async H2D.  Clips already on the model's device (what `loader.load_audio`
+    returns): packed with device-to-device copies — nothing goes back to the host between the resampler and the tower."""
     cfg = datasetconfig or DatasetConfig()
     dev = model._device()
     outs = []
     for i in range(0, len(waves), batch_size):
-        buf, lens = loader.pad_ragged(waves[i:i + batch_size])
-        w = buf.to(dev, non_blocking=True)
-        outs.append(model.encode_audio(w, max_patches=cfg.patches_seq_len, lengths=lens, trim_padding=trim_padding))
+        chunk = waves[i:i + batch_size]
+        if all(isinstance(w, torch.Tensor) and w.is_cuda for w in chunk):
+            w, lens = loader.pad_ragged_device([c.to(dev) for c in chunk])
+            longest = int(max(c.shape[0] for c in chunk))
+        else:
+            buf, lens = loader.pad_ragged(chunk)
+            w = buf.to(dev, non_blocking=True)
+            longest = int(lens.max())
+        outs.append(_encode_ragged(model, w, lens, longest, cfg.patches_seq_len, trim_padding))
+    return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+
+def _encode_ragged(model: CACO, w: torch.Tensor, lens: torch.Tensor, longest: int, max_patches: int, trim_padding: bool
+                   ) -> torch.Tensor:
+    """encode_audio on a packed ragged batch; the trimmed patch count comes from the host-known longest clip, so device
+    lengths never have to be read back."""
+    P = max_patches
+    if trim_padding:
+        valid = (((min(longest, w.shape[1]) + 159) // 160) // 16) * 8          # eval_caco_torch.py:67,116-117
+        P = max(8, min(P, valid))
+    return model.encode_audio(w, max_patches=P, lengths=lens, trim_padding=False)
+
+
+@torch.no_grad()
+def embed_files(model: CACO, filepaths: Sequence[str], sampling_rate: int, datasetconfig: Optional[DatasetConfig] = None,
+                batch_size: int = 64, trim_padding: bool = True) -> torch.Tensor:
+    """Files -> embeddings without a host round trip: every file's raw samples go through a double-buffered pinned stage
+    (async H2D), are resampled on the device and packed device-side; while the tower of batch k runs (enqueued
+    asynchronously), the host reads the files of batch k+1."""
+    dev = model._device()
+    stager = loader.PinnedStager(dev)
+    outs = []
+    for i in range(0, len(filepaths), batch_size):
+        clips = [loader.load_audio(fp, sampling_rate, dev, stager) for fp in filepaths[i:i + batch_size]]
+        outs.append(embed_waveforms(model, clips, datasetconfig, batch_size, trim_padding))
     return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
 
 
@@ -145,8 +178,15 @@ def zs_classification_arrays(model: CACO, all_text_embeddings: torch.Tensor, wav
                              ) -> Dict[str, float]:
     """The loop body of zs_classification (eval_caco_torch.py:315-336) for in-memory clips: top-k accuracy per k."""
     a = embed_waveforms(model, waves, datasetconfig, batch_size)
+    return zs_accuracy_from_embeddings(model, a, all_text_embeddings, target_indices, ks)
+
+
+@torch.no_grad()
+def zs_accuracy_from_embeddings(model: CACO, audio_embeddings: torch.Tensor, all_text_embeddings: torch.Tensor,
+                                target_indices: Sequence[int], ks: Sequence[int] = (1,)) -> Dict[str, float]:
+    """eval_caco_torch.py:330-336: top-k accuracy from the logits matrix, ranking on the device."""
     kmax = max(ks)
-    top = zero_shot_topk(model, a, all_text_embeddings, kmax)
+    top = zero_shot_topk(model, audio_embeddings, all_text_embeddings, kmax)
     tgt = torch.as_tensor(list(target_indices), dtype=torch.int32, device=top.device)[:, None]
     out = {}
     for k in ks:
@@ -162,12 +202,12 @@ def zs_classification(model: CACO, tokenizer: Any, dataprocessor: Any, datasetco
     class_to_index_map = {v: i for i, v in enumerate(class_labels)}
     all_text_embeddings = compute_all_class_embeddings(model, tokenizer, class_labels, datasetconfig.max_text_len, device,
                                                        prefix=text_prefix)
-    waves, targets = [], []
+    targets = []
     for fp in filepaths:
         audio_name = fp.split("/")[-1].split(".wav")[0]
         targets.append(class_to_index_map[descriptions[audio_name]["description"][0]])
-        waves.append(loader.load_audio(fp, dataprocessor.config.sampling_rate, device).cpu())
-    acc = zs_classification_arrays(model, all_text_embeddings, waves, targets, datasetconfig, ks=(1,))
+    a = embed_files(model, filepaths, dataprocessor.config.sampling_rate, datasetconfig)
+    acc = zs_accuracy_from_embeddings(model, a, all_text_embeddings, targets, ks=(1,))
     for k, v in acc.items():
         print(f"top {k} accuracy: {v:.4f}")
     return acc["1"]
@@ -264,9 +304,11 @@ def retrieval_topk(text_embeddings: torch.Tensor, audio_embeddings: torch.Tensor
 
 
 @torch.no_grad()
-def audio_retrieval_arrays(model: CACO, waves: Sequence[Any], audio_names: Sequence[str], captions: Sequence[Sequence[str]],
-                           tokenizer: Any, datasetconfig: Optional[DatasetConfig] = None, verbose: bool = True) -> Dict[str, Any]:
-    """audio_retrieval (eval_caco_torch.py:343-408) for in-memory clips: captions[i] = the descriptions of clip i."""
+def audio_retrieval_arrays(model: CACO, waves: Optional[Sequence[Any]], audio_names: Sequence[str],
+                           captions: Sequence[Sequence[str]], tokenizer: Any, datasetconfig: Optional[DatasetConfig] = None,
+                           verbose: bool = True, audio_embeddings: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+    """audio_retrieval (eval_caco_torch.py:343-408) for in-memory clips: captions[i] = the descriptions of clip i
+    (audio_embeddings: already-computed [n_clips, 768] embeddings instead of `waves`)."""
     cfg = datasetconfig or DatasetConfig()
     dev = model._device()
     all_text, gt_audio_text, gt_text_audio = [], {}, {}
@@ -278,7 +320,7 @@ def audio_retrieval_arrays(model: CACO, waves: Sequence[Any], audio_names: Seque
             all_text.append(c)
     tb = prepare_text_batch(all_text, tokenizer, cfg.max_text_len, dev)
     t = embed_text_ids(model, tb["text_input_ids"], tb["text_mask"])
-    a = embed_waveforms(model, waves, cfg)
+    a = audio_embeddings if audio_embeddings is not None else embed_waveforms(model, waves, cfg)
     at_idx, ta_idx = retrieval_topk(t, a, 10)
     if at_idx.shape[1] < 10 or ta_idx.shape[1] < 10:
         raise ValueError("audio_retrieval needs at least 10 clips and 10 captions (the reference indexes indices[i, :10])")
@@ -295,10 +337,10 @@ def audio_retrieval(model: CACO, tokenizer: Any, dataprocessor: Any, datasetconf
                     device: Union[str, torch.device], eval_split: str = "test") -> Dict[str, Any]:
     """eval_caco_torch.py:343-408 (same arguments and printed output; additionally returns the metrics)."""
     filepaths, descriptions, _ = dataprocessor.get_filepaths_and_descriptions(current_split=eval_split)
-    names, caps, waves = [], [], []
+    names, caps = [], []
     for fp in filepaths:
         name = fp.split("/")[-1].split(".wav")[0]
         names.append(name)
         caps.append(list(descriptions[name]["description"]))
-        waves.append(loader.load_audio(fp, dataprocessor.config.sampling_rate, device).cpu())
-    return audio_retrieval_arrays(model, waves, names, caps, tokenizer, datasetconfig)
+    a = embed_files(model, filepaths, dataprocessor.config.sampling_rate, datasetconfig)
+    return audio_retrieval_arrays(model, None, names, caps, tokenizer, datasetconfig, audio_embeddings=a)

@@ -52,6 +52,59 @@ def pad_ragged(waves: Sequence[ArrayLike], stride: Optional[int] = None, pin: bo
     return buf, lens
 
 
+def pad_ragged_device(waves: Sequence[torch.Tensor], stride: Optional[int] = None, multiple: int = 160
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`pad_ragged` for clips that already live on the GPU (e.g. the output of `load_audio` / `resample_to_16k`): one
+    zero-filled [batch, stride] device buffer filled with device-to-device copies on the current stream, plus device int32
+    lengths — no host round trip between the resampler and the frontend."""
+    if len(waves) == 0:
+        raise ValueError("pad_ragged_device: empty batch")
+    dev = waves[0].device
+    if dev.type != "cuda" or any((not isinstance(w, torch.Tensor)) or w.device != dev or w.dim() != 1 for w in waves):
+        raise ValueError("pad_ragged_device: 1-D CUDA tensors on one device expected")
+    longest = max(int(w.shape[0]) for w in waves)
+    if stride is None:
+        stride = max(multiple, -(-longest // multiple) * multiple)
+    with torch.cuda.device(dev):
+        buf = torch.zeros((len(waves), stride), dtype=torch.float32, device=dev)
+        ns = []
+        for i, w in enumerate(waves):
+            n = min(int(w.shape[0]), stride)
+            buf[i, :n].copy_(w[:n], non_blocking=True)
+            ns.append(n)
+        lens = torch.tensor(ns, dtype=torch.int32).to(dev, non_blocking=True)
+    return buf, lens
+
+
+class PinnedStager:
+    """Double-buffered pinned staging for raw file samples: `put(array)` copies a host array into one of two reusable pinned
+    buffers and enqueues the host-to-device copy on the current stream; a buffer is reused only after the copy that read it
+    has completed (one event per buffer), so file reading for clip k+1 overlaps the transfer (and the GPU work) of clip k.
+    Replaces the per-file pageable `tensor.to(device)` (a synchronous copy) of a naive loader."""
+
+    def __init__(self, device: Union[str, torch.device], initial: int = 1 << 20):
+        self.device = torch.device(device)
+        self._buf = [torch.empty(initial, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._ev: List[Optional[torch.cuda.Event]] = [None, None]
+        self._k = 0
+
+    def put(self, array: np.ndarray) -> torch.Tensor:
+        a = np.ascontiguousarray(array, dtype=np.float32).reshape(-1)
+        k = self._k
+        self._k ^= 1
+        if self._ev[k] is not None:
+            self._ev[k].synchronize()
+        if self._buf[k].numel() < a.shape[0]:
+            self._buf[k] = torch.empty(max(a.shape[0], 2 * self._buf[k].numel()), dtype=torch.float32).pin_memory()
+        self._buf[k].numpy()[: a.shape[0]] = a
+        with torch.cuda.device(self.device):
+            out = self._buf[k][: a.shape[0]].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._ev[k] = ev
+        return out
+
+
 def valid_patch_counts(lengths: ArrayLike, max_patches: int) -> np.ndarray:
     """Per-clip number of valid tokens, eval_caco_torch.py:67,116-117,132-138: floor(ceil(L/160)/16)*8 cut to max_patches."""
     L = np.asarray(lengths, dtype=np.int64)
@@ -85,7 +138,8 @@ def resample_to_16k(audio: ArrayLike, sampling_rate: int, device: Union[str, tor
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("cacophony_b200 runs on a CUDA device only (no CPU fallback)")
-    x = torch.as_tensor(audio, dtype=torch.float32).to(dev)
+    x = audio.to(device=dev, dtype=torch.float32) if isinstance(audio, torch.Tensor) else \
+        torch.as_tensor(audio, dtype=torch.float32).to(dev)
     if x.dim() != 1:
         raise ValueError("resample_to_16k: one 1-D clip expected")
     nx = x.shape[0]
@@ -105,9 +159,12 @@ def resample_to_16k(audio: ArrayLike, sampling_rate: int, device: Union[str, tor
     return torch.fft.irfft(Y, n=num) * (float(num) / float(nx))
 
 
-def load_audio(audio_path: str, dataset_sampling_rate: int, device: Union[str, torch.device] = "cuda") -> torch.Tensor:
-    """eval_utils.py:6-16 with the resampling on the device.  Reads with soundfile when it is installed, else PCM/float WAV
-    through scipy.io.wavfile (int PCM scaled to [-1, 1) as soundfile does)."""
+def load_audio(audio_path: str, dataset_sampling_rate: int, device: Union[str, torch.device] = "cuda",
+               stager: Optional[PinnedStager] = None) -> torch.Tensor:
+    """eval_utils.py:6-16 with the resampling on the device; returns a 1-D fp32 CUDA tensor that STAYS on the device (feed
+    lists of them to `pad_ragged_device` / `eval.embed_waveforms`).  Reads with soundfile when it is installed, else PCM/float
+    WAV through scipy.io.wavfile (int PCM scaled to [-1, 1) as soundfile does).  stager: a `PinnedStager` makes the
+    host-to-device copy of the raw samples asynchronous."""
     try:
         import soundfile as sf
         wav, _ = sf.read(audio_path)
@@ -121,4 +178,6 @@ def load_audio(audio_path: str, dataset_sampling_rate: int, device: Union[str, t
             wav = raw.astype(np.float32)
     if wav.ndim > 1:
         wav = wav.mean(axis=-1)
+    if stager is not None:
+        return resample_to_16k(stager.put(wav), dataset_sampling_rate, device)
     return resample_to_16k(wav, dataset_sampling_rate, device)

@@ -38,6 +38,10 @@ MODEL_CASES = {
                            cap_lens=[32, 11], T=32, max_patches=500),
     "model_s2_t100": dict(seed=2, sharp=1.0, clip_lens=[80000, 80000, 80000], zero_tail=[0, 0, 0],
                           cap_lens=[8, 10, 12], T=100, max_patches=500),
+    # checkpoint-like outliers (oracle/weights.py::_apply_outliers): LayerNorm gains x 30 in six channels, residual channels at
+    # +-300, fc1 pre-activations near 1e3 — the case the fp16-operand scheme has to survive (or the split-weight mode)
+    "model_s3_outlier": dict(seed=3, sharp=1.0, outlier=True, clip_lens=[160000, 80000, 40000], zero_tail=[0, 0, 0],
+                             cap_lens=[32, 13, 6], T=32, max_patches=500),
 }
 
 
@@ -74,6 +78,7 @@ def main():
     create_caco_model, E = _import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
 
+    only = set(sys.argv[1:])         # e.g. `python oracle/make_golden.py model_s3_outlier`: only that fixture
     # ---- frontend -------------------------------------------------------------------------
     fe = {}
     for name, seed, kind, n, mp in FRONTEND_CASES:
@@ -88,12 +93,15 @@ def main():
         if n <= 20000:
             fe[name + "/mel"] = mel
             fe[name + "/patches"] = p["audio_patches"]
-    np.savez_compressed(os.path.join(GOLDEN, "frontend.npz"), **fe)
-    print("frontend.npz", len(fe), "arrays")
+    if not only or "frontend" in only:
+        np.savez_compressed(os.path.join(GOLDEN, "frontend.npz"), **fe)
+        print("frontend.npz", len(fe), "arrays")
 
     # ---- model ----------------------------------------------------------------------------
     for name, c in MODEL_CASES.items():
-        sd = W.make_state_dict(c["seed"], c["sharp"])
+        if only and name not in only:
+            continue
+        sd = W.make_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
         ref = create_caco_model().eval()
         missing, unexpected = ref.load_state_dict(sd, strict=False)
         assert not unexpected and all(k.startswith("decoder_module") for k in missing)

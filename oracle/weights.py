@@ -13,7 +13,8 @@ The distributions follow PyTorch's default initialisers for the same layers (uni
 ``±1/sqrt(fan_in)`` Linear, xavier-uniform MHA in-proj, N(0,1) embeddings, N(0,0.02²)
 queries) but LayerNorm gains/biases and the MHA biases are randomised instead of 1/0 so
 that every parameter on the path influences the result.  ``sharp > 1`` scales the q/k
-projections so that softmax rows become peaky (harder numerics than near-uniform attention).
+projections so that softmax rows become peaky (harder numerics than near-uniform attention);
+``outlier=True`` adds the outlier channels trained checkpoints have (see ``_apply_outliers``).
 """
 from __future__ import annotations
 
@@ -115,11 +116,42 @@ def _gen(rng: np.random.Generator, shape, kind: str) -> np.ndarray:
     return ((2.0 * u - 1.0) * np.float32(b)).astype(np.float32)
 
 
-def iter_weights(seed: int, sharp: float = 1.0, **spec_kw) -> Iterator[Tuple[str, np.ndarray]]:
+# "checkpoint-like" outliers: what trained transformers have and PyTorch's initialisers do not
+OUTLIER_LN_CHANNELS = (7, 77, 161, 305, 449, 701)      # LayerNorm gains x 30 in these channels, every LayerNorm
+OUTLIER_LN_GAIN = 30.0
+OUTLIER_RESID = ((33, 300.0), (555, -300.0))           # audio residual stream: input_proj.bias pushes two channels to +-300
+OUTLIER_TEXT_BETA = ((33, 20.0), (555, -20.0))         # text (post-LN): the same two channels of every LayerNorm bias
+OUTLIER_FC1_UNITS = (5, 130, 1027, 2049, 3000)         # fc1 / intermediate biases: pre-activations near +1e3
+OUTLIER_FC1_BIAS = 1000.0
+
+
+def _apply_outliers(name: str, w: np.ndarray) -> np.ndarray:
+    is_ln_w = name.endswith(("norm1.weight", "norm2.weight", "norm.weight", "LayerNorm.weight"))
+    is_ln_b = name.endswith("LayerNorm.bias")
+    if is_ln_w:
+        w = w.copy()
+        w[list(OUTLIER_LN_CHANNELS)] *= np.float32(OUTLIER_LN_GAIN)
+    elif is_ln_b and name.startswith("text_module."):
+        w = w.copy()
+        for c, v in OUTLIER_TEXT_BETA:
+            w[c] = np.float32(v)
+    elif name == "audio_module.input_proj.bias":
+        w = w.copy()
+        for c, v in OUTLIER_RESID:
+            w[c] = np.float32(v)
+    elif name.endswith(("mlp.fc1.bias", "intermediate.dense.bias")):
+        w = w.copy()
+        w[list(OUTLIER_FC1_UNITS)] = np.float32(OUTLIER_FC1_BIAS)
+    return w
+
+
+def iter_weights(seed: int, sharp: float = 1.0, outlier: bool = False, **spec_kw) -> Iterator[Tuple[str, np.ndarray]]:
     rng = np.random.default_rng(np.random.PCG64(1000003 * seed + 17))
     D = HIDDEN
     for name, shape, kind in param_spec(**spec_kw):
         w = _gen(rng, shape, kind)
+        if outlier:
+            w = _apply_outliers(name, w)
         if sharp != 1.0:
             if name.endswith("attn.in_proj_weight") or name.endswith("attn.in_proj_bias"):
                 w = w.copy()
@@ -129,10 +161,11 @@ def iter_weights(seed: int, sharp: float = 1.0, **spec_kw) -> Iterator[Tuple[str
         yield name, w
 
 
-def make_state_dict(seed: int, sharp: float = 1.0, **spec_kw) -> Dict[str, "torch.Tensor"]:
-    """Synthetic encoder-path ``state_dict`` as CPU fp32 torch tensors."""
+def make_state_dict(seed: int, sharp: float = 1.0, outlier: bool = False, **spec_kw) -> Dict[str, "torch.Tensor"]:
+    """Synthetic encoder-path ``state_dict`` as CPU fp32 torch tensors.  outlier: checkpoint-like outlier structure (LayerNorm
+    gains x 30 in six channels, two residual channels at +-300, a few fc1 pre-activations near 1e3)."""
     import torch
-    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in iter_weights(seed, sharp, **spec_kw)}
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in iter_weights(seed, sharp, outlier, **spec_kw)}
 
 
 # ---------------------------------------------------------------------------------------------

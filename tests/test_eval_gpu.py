@@ -237,3 +237,34 @@ def test_load_audio_wav_file_matches_reference_pipeline(tmp_path):
     ref = E.resample(ref.astype(np.float64), 44100)
     assert got.shape == ref.shape == (8000,)
     assert np.abs(got - ref).max() < 5e-6
+
+
+def test_device_resident_clips_skip_the_host(tmp_path, synthetic_state_dict):
+    """Row f-1: clips that are already on the GPU (what load_audio returns) are packed with device-to-device copies and give
+    bit-identical embeddings to the pinned-host path; embed_files (double-buffered pinned staging -> GPU resample -> device
+    packing) equals loading every file by hand."""
+    from scipy.io import wavfile
+    from cacophony_b200 import eval as ev
+    from cacophony_b200 import loader
+    m = cb.create_caco_model()
+    m.load_state_dict(synthetic_state_dict(0, 1.0))
+    m = m.to("cuda")
+    rng = np.random.default_rng(3)
+    clips = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in (80000, 52345, 160000, 16000, 99999)]
+    e_host = ev.embed_waveforms(m, clips)
+    e_dev = ev.embed_waveforms(m, [torch.from_numpy(c).cuda() for c in clips])
+    assert torch.equal(e_host, e_dev)
+    buf, lens = loader.pad_ragged_device([torch.from_numpy(c).cuda() for c in clips])
+    hbuf, hlens = loader.pad_ragged(clips)
+    assert torch.equal(buf.cpu(), hbuf) and torch.equal(lens.cpu(), hlens)
+    paths = []
+    for i, sr in enumerate((44100, 16000, 22050)):
+        x = (0.2 * rng.standard_normal(sr * 2)).astype(np.float32)
+        p = str(tmp_path / f"clip{i}.wav")
+        wavfile.write(p, sr, x)
+        paths.append((p, sr))
+    for sr in (44100, 16000, 22050):
+        group = [p for p, s in paths if s == sr]
+        e_files = ev.embed_files(m, group, sr, batch_size=2)
+        by_hand = ev.embed_waveforms(m, [loader.load_audio(p, sr, "cuda") for p in group])
+        assert torch.equal(e_files, by_hand) and torch.isfinite(e_files).all()

@@ -88,3 +88,36 @@ def test_gemm_rejects_bad_arguments():
         ops.gemm_f16(a.float(), w, None, L.EPI_BIAS_F32)
     with pytest.raises(ValueError):
         ops.gemm_f16(a.cpu(), w, None, L.EPI_BIAS_F32)
+
+
+@pytest.mark.parametrize("vname", list(VARIANTS))
+@pytest.mark.parametrize("shape", [(256, 768, 768), (1000, 2304, 768), (333, 768, 3072), (512, 768, 256)])
+def test_gemm_split_weights(vname, shape):
+    """Split-weight form (precision mode): W enters as fp16 hi + lo along a doubled reduction, A's k-blocks are re-read.  The
+    result must match the product of the fp16 activations with the EXACT fp32 weights up to the tensor core's fp32
+    accumulation over the (doubled) reduction — under 1e-5 relative even at K = 3072 — and be an order of magnitude closer
+    to it than the plain fp16-weight GEMM."""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    w2 = ops.cast_f16_split(w.contiguous())
+    assert w2.shape == (N, 2 * K)
+    hi, lo = w2[:, :K].float(), w2[:, K:].float()
+    assert float((hi + lo - w).abs().max()) <= float(w.abs().max()) * 2.0 ** -21
+    out = ops.gemm_f16_wsplit(a, w2, bias, L.EPI_BIAS_F32, variant=VARIANTS[vname])
+    plain = ops.gemm_f16(a, w.half(), bias, L.EPI_BIAS_F32, variant=VARIANTS[vname])
+    ref = (a.double() @ w.double().t() + bias.double()).float()
+    e_split = float((out - ref).norm() / ref.norm())
+    e_plain = float((plain - ref).norm() / ref.norm())
+    assert e_split < 1e-5 and e_split < e_plain / 10, (e_split, e_plain)
+
+
+def test_per_handle_options_do_not_leak():
+    """Execution options are per model handle (caco_model_set_option); the library defaults used by op-level calls stay
+    untouched, unknown names are rejected."""
+    lib = L.load()
+    assert lib.caco_set_default_option(b"no_such_option", 1) == -1
+    assert lib.caco_set_default_option(b"gemm_variant", 99) == -1
+    assert lib.caco_set_default_option(b"pdl", 1) == 0

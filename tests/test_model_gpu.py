@@ -10,6 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import cacophony_b200 as cb
+from cacophony_b200 import _lib as L
 from oracle import caco_oracle as O
 from oracle import weights as W
 from oracle.make_golden import MODEL_CASES, case_inputs
@@ -22,12 +23,12 @@ REL_TOL = 1e-3          # BASELINE.json north_star: embeddings and logits within
 _MODELS = {}
 
 
-def _model(seed, sharp, synthetic_state_dict):
-    key = (seed, sharp)
+def _model(seed, sharp, synthetic_state_dict, outlier=False):
+    key = (seed, sharp, outlier)
     if key not in _MODELS:
         _MODELS.clear()
         m = cb.create_caco_model()
-        m.load_state_dict(synthetic_state_dict(seed, sharp))
+        m.load_state_dict(synthetic_state_dict(seed, sharp, outlier))
         _MODELS[key] = m.to("cuda")
     return _MODELS[key]
 
@@ -42,10 +43,11 @@ def _audio_batch(waves, max_patches):
 def test_model_matches_reference_golden(name, golden_dir, synthetic_state_dict):
     c = MODEL_CASES[name]
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict, c.get("outlier", False))
     waves, ids, mask = case_inputs(c)
     ab = _audio_batch(waves, c["max_patches"])
     ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    L.load().caco_saturation_count(1)
 
     a_raw, a_hid = model.get_audio_embedding(**ab)
     a_n = model.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
@@ -74,15 +76,76 @@ def test_model_matches_reference_golden(name, golden_dir, synthetic_state_dict):
     if "at_logits" in g.files:
         at, ta = model(**ab, text_input_ids=ids_t, text_mask=mask_t)
         scale = float(np.exp(W.LOGIT_SCALE_INIT))
-        # logits are scale * cosine: 1e-3 relative on unit-norm embeddings = 1e-3 * scale absolute
+        # Logits are exp(logit_scale) * cosine.  The bar that follows from 1e-3-accurate unit-norm embeddings is an error of
+        # 1e-3 in the COSINE, i.e. 1e-3 * exp(logit_scale) absolute on every logit: asserted.  The row-relative error is
+        # reported too, but on these random-weight models audio and text embeddings are nearly orthogonal (|cos| ~ 0.02, logits
+        # ~ 0.3 of a possible 14.3), where a relative error divides by almost nothing: measured 0.8e-3 .. 3.4e-3 on these rows
+        # with embeddings at 4-6e-4 (B200, round 2).  Where the logits are well conditioned (the audio-audio and text-text
+        # similarity matrices below, diagonal = exp(logit_scale)) the row-relative error IS held to 1e-3.
+        e_at, e_ta = rel_rows(at, g["at_logits"]), rel_rows(ta, g["ta_logits"])
+        print(name, "logits row-relative error", e_at, e_ta)
         assert np.abs(at.cpu().numpy() - g["at_logits"]).max() < REL_TOL * scale
         assert np.abs(ta.cpu().numpy() - g["ta_logits"]).max() < REL_TOL * scale
-        assert rel_rows(at, g["at_logits"]) < 5 * REL_TOL or np.abs(at.cpu().numpy() - g["at_logits"]).max() < 2e-3
+        assert e_at < 5 * REL_TOL and e_ta < 5 * REL_TOL, (e_at, e_ta)
+        for ours, ref in ((a_n, g["audio_emb"]), (t_n, g["text_emb"])):
+            self_sim, _ = model.similarity(ours, ours, want_ta=False)
+            ref_t = torch.from_numpy(ref)
+            ref_sim = (scale * ref_t) @ ref_t.T
+            e_self = rel_rows(self_sim, ref_sim)
+            print(name, "self-similarity logits row-relative error", e_self)
+            assert e_self < REL_TOL, e_self
+    assert L.load().caco_saturation_count(0) == 0            # no fp16 operand copy had to be clamped to +-65504
     zs = torch.exp(model.logit_scale) * a_n @ t_n.T
     assert np.abs(zs.cpu().numpy() - g["zs_logits"]).max() < REL_TOL * float(np.exp(W.LOGIT_SCALE_INIT))
     margin = np.sort(g["zs_logits"], -1)
     clear = (margin[:, -1] - margin[:, -2]) > 2e-2 if margin.shape[1] > 1 else np.ones(len(margin), bool)
     assert np.array_equal(zs.argmax(-1).cpu().numpy()[clear], g["zs_top1"][clear])
+
+
+@pytest.mark.parametrize("name", ["model_s0", "model_s3_outlier"])
+def test_split_weight_precision_mode(name, golden_dir, synthetic_state_dict):
+    """The precision escape hatch: with ``split_weights`` every GEMM weight enters as fp16 hi + lo (two
+    accumulating tensor-core passes).  On the default and on the checkpoint-like outlier model it must meet the 1e-3 bar and
+    lower the audio-embedding error of the default fp16-operand scheme (activation rounding, which it does not touch, is
+    the larger share of it; both errors are printed); switching back restores the default result bit for bit.  An activation
+    forced past the fp16 range is clamped and reported by the saturation counter instead of turning into inf."""
+    c = MODEL_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict, c.get("outlier", False))
+    waves, ids, mask = case_inputs(c)
+    ab = _audio_batch(waves, c["max_patches"])
+    ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+
+    def run():
+        a = model.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
+        t = model.get_text_embedding(ids_t, mask_t, return_hidden_state=False, normalize=True)
+        return a, t
+    a0, t0 = run()
+    gen0 = model.generation()
+    model.set_option("split_weights", 1)
+    a1, t1 = run()
+    assert model.generation() > gen0                       # the weight arena was re-packed
+    model.set_option("split_weights", 0)
+    a2, t2 = run()
+    errs = {"default": (rel_rows(a0, g["audio_emb"]), rel_rows(t0, g["text_emb"])),
+            "split_weights": (rel_rows(a1, g["audio_emb"]), rel_rows(t1, g["text_emb"]))}
+    print(name, errs)
+    assert max(errs["split_weights"]) < REL_TOL and max(errs["default"]) < REL_TOL
+    assert errs["split_weights"][0] < errs["default"][0]
+    assert torch.equal(a0, a2) and torch.equal(t0, t2)
+    # saturation guard: scale fc1 of one audio layer so that SiLU outputs leave the fp16 range
+    L.load().caco_saturation_count(1)
+    w = model.audio_module.layers[0].mlp.fc1
+    old = w.bias.data.clone()
+    w.bias.data[5] = 1.0e6
+    model.repack()
+    a3, _ = run()
+    assert L.load().caco_saturation_count(1) > 0
+    assert torch.isfinite(a3).all()
+    w.bias.data.copy_(old)
+    model.repack()
+    a4, _ = run()
+    assert torch.equal(a4, a0) and L.load().caco_saturation_count(1) == 0
 
 
 def test_encode_audio_alias_equals_two_step(synthetic_state_dict):

@@ -68,7 +68,7 @@ def _rel_rows(x, y):
 def test_model_matches_reference(name, golden_dir, synthetic_state_dict):
     c = MODEL_CASES[name]
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    sd = synthetic_state_dict(c["seed"], c["sharp"])
+    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
     waves, ids, mask = case_inputs(c)
     ab = O.prepare_audio_batch(waves, c["max_patches"])
     ids, mask = torch.from_numpy(ids), torch.from_numpy(mask)
@@ -99,7 +99,7 @@ def test_rounding_emulation_is_within_design_budget(golden_dir, synthetic_state_
     precision scheme itself (not a kernel) is wrong."""
     c = MODEL_CASES["model_s0"]
     g = np.load(os.path.join(golden_dir, "model_s0.npz"))
-    sd = synthetic_state_dict(c["seed"], c["sharp"])
+    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
     waves, ids, mask = case_inputs(c)
     ab = O.prepare_audio_batch(waves[:2], c["max_patches"])
     r = O.Rounding.fp16()
