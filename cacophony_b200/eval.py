@@ -30,15 +30,23 @@ from .model import CACO, create_caco_model
 
 # ----------------------------------------------------------------------------------------------------------- loading
 def load_caco_torch(ckpt_path: Optional[str], device: Union[str, torch.device], tokenizer: Any = None,
-                    state_dict: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, Any]:
+                    state_dict: Optional[Dict[str, torch.Tensor]] = None, pool_heads: Optional[int] = None) -> Dict[str, Any]:
     """eval_caco_torch.py:154-178.  Accepts the three checkpoint layouts the reference accepts ('model_state_dict',
-    'state_dict', or a bare state_dict); ``decoder_module.*`` tensors are ignored.  The tokenizer cannot be downloaded here:
-    pass one in (``RobertaTokenizerFast.from_pretrained('roberta-base')`` where the files exist)."""
-    model = create_caco_model()
+    'state_dict', or a bare state_dict) and, beyond the reference, the original Flax checkpoint file (msgpack, converted on
+    the fly by ``checkpoint.convert_caco_checkpoint``); ``decoder_module.*`` tensors are ignored.  pool_heads: audio pooler
+    head count if not the torch port's 2 (the JAX loader uses 8, load_model.py:47).  The tokenizer cannot be downloaded
+    here: pass one in (``RobertaTokenizerFast.from_pretrained('roberta-base')`` where the files exist)."""
+    from . import checkpoint as ckpt
+    model = create_caco_model() if pool_heads is None else create_caco_model(num_attention_pool_heads=pool_heads)
     if state_dict is None:
         if ckpt_path is None:
             raise ValueError("load_caco_torch: ckpt_path or state_dict required")
-        checkpoint = torch.load(ckpt_path, map_location="cpu")
+        with open(ckpt_path, "rb") as f:
+            head = f.read(4)
+        if head[:2] == b"PK" or head[:1] == b"\x80":            # torch.save: zip archive (or legacy pickle)
+            checkpoint = torch.load(ckpt_path, map_location="cpu")
+        else:                                                    # flax.training.checkpoints: msgpack
+            checkpoint = ckpt.convert_caco_checkpoint(ckpt_path)
     else:
         checkpoint = state_dict
     if "model_state_dict" in checkpoint:

@@ -514,12 +514,13 @@ def _as(t: torch.Tensor, dtype, dev, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def create_caco_model() -> CACO:
-    """caco.py:264-317: the checkpoint's configuration."""
+def create_caco_model(num_attention_pool_heads: int = 2) -> CACO:
+    """caco.py:264-317: the checkpoint's configuration (num_attention_pool_heads: 2 as the torch port builds it, caco.py:292;
+    the JAX loader uses 8, load_model.py:47 — same parameter shapes)."""
     audio_config = AudioTransformerConfig(hidden_size=768, num_layers=12, num_heads=8, intermediate_size=3072,
                                           patch_size=256, max_time_ind=512, num_freq_patches=8, dropout_rate=0.0,
                                           drop_path_rate=0.0)
     text_config = RobertaConfig()
-    caco_config = CACOConfig()
+    caco_config = CACOConfig(num_attention_pool_heads=num_attention_pool_heads)
     decoder_config = RobertaConfig(num_hidden_layers=4)
     return CACO(audio_config=audio_config, text_config=text_config, caco_config=caco_config, decoder_config=decoder_config)

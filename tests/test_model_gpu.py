@@ -148,6 +148,54 @@ def test_split_weight_precision_mode(name, golden_dir, synthetic_state_dict):
     assert torch.equal(a4, a0) and L.load().caco_saturation_count(1) == 0
 
 
+def test_eight_pooler_heads_and_flax_checkpoint_file(tmp_path, synthetic_state_dict):
+    """Row f-3 on the GPU: the parameters go out as a Flax-layout msgpack checkpoint file and come back through
+    ``load_caco_torch(path, pool_heads=8)`` (the JAX configuration's head count, load_model.py:47) and through a torch.save'd
+    ``{'model_state_dict': ...}`` file; the 8-head model matches the CPU oracle run with 8 pooler heads, the 2-head model
+    loaded from the file equals the model built from the state_dict directly."""
+    import cacophony_b200.checkpoint as ck
+    from cacophony_b200 import eval as ev
+    c = MODEL_CASES["model_s0"]
+    sd = synthetic_state_dict(c["seed"], c["sharp"])
+    flax_path, torch_path = str(tmp_path / "Cacophony.ckpt"), str(tmp_path / "caco_torch.pt")
+    ck.write_flax_msgpack({"0": {"params": ck.flax_tree_from_state_dict(sd, audio_heads=8, scan=True)}}, flax_path)
+    torch.save({"model_state_dict": sd}, torch_path)
+    waves, ids, mask = case_inputs(c)
+    ab = _audio_batch(waves[:2], c["max_patches"])
+    m8 = ev.load_caco_torch(flax_path, "cuda", pool_heads=8)["model"]
+    a8 = m8.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
+    rb = O.prepare_audio_batch(waves[:2], c["max_patches"])
+    ref8, _ = O.get_audio_embedding(sd, rb["audio_patches"], rb["audio_time_inds"], rb["audio_freq_inds"], rb["audio_mask"],
+                                    normalize=True, pool_heads=8)
+    assert rel_rows(a8, ref8) < REL_TOL
+    m2 = ev.load_caco_torch(torch_path, "cuda")["model"]
+    a2 = m2.get_audio_embedding(**ab, return_hidden_state=False, normalize=True)
+    direct = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    assert torch.equal(a2, direct.get_audio_embedding(**ab, return_hidden_state=False, normalize=True))
+    assert rel_rows(a2, a8) > 1e-3                       # the head count does change the embedding
+    del m8, m2
+
+
+def test_copies_of_a_model_own_their_handles(synthetic_state_dict):
+    """copy.deepcopy / pickle of a CACO never share the C handle: the copy packs its own weights and keeps working
+    after the original is gone."""
+    import copy
+    import pickle
+    c = MODEL_CASES["model_s0"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    ids, mask = W.make_captions(3, 2, 16, lens=[16, 7])
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    t0 = model.encode_text(ids, mask)
+    twin = copy.deepcopy(model)
+    assert twin._handle is None and model._handle is not None
+    assert torch.equal(twin.encode_text(ids, mask), t0) and twin._handle != model._handle
+    revived = pickle.loads(pickle.dumps(model))
+    assert revived._handle is None
+    assert torch.equal(revived.encode_text(ids, mask), t0)
+    del twin, revived
+    assert torch.equal(model.encode_text(ids, mask), t0)
+
+
 def test_encode_audio_alias_equals_two_step(synthetic_state_dict):
     c = MODEL_CASES["model_s0"]
     model = _model(c["seed"], c["sharp"], synthetic_state_dict)

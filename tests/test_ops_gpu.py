@@ -175,6 +175,26 @@ def test_attn_pool_matches_direct_formula(with_ln):
         np.testing.assert_allclose(hid_out.cpu().numpy(), hn.numpy(), atol=3e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("H", [1, 3, 5, 8])
+def test_attn_pool_head_counts(H):
+    """1..8 pooler heads (the JAX configuration uses 8, src/caco/load_model.py:47; more than four take a second pass)."""
+    g = torch.Generator().manual_seed(40 + H)
+    B, S, D = 2, 300, 768
+    hid = torch.randn(B, S, D, generator=g)
+    mask = torch.ones(B, S)
+    mask[1, 200:] = 0
+    u, c = torch.randn(H, D, generator=g) * 0.05, torch.randn(H, generator=g)
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    hn = O.layer_norm(hid, gamma, beta)
+    s = torch.einsum("hd,bjd->bhj", u, hn) + c[None, :, None]
+    s = s.masked_fill((mask == 0)[:, None, :], float("-inf"))
+    ref = torch.einsum("bhj,bjd->bhd", torch.softmax(s, -1), hn)
+    pooled, hid_out = ops.attn_pool(hid.cuda(), mask.cuda(), u.cuda(), c.cuda(), gamma.cuda(), beta.cuda(), 1e-5, want_hidden=True)
+    assert pooled.shape == (B, H, D)
+    np.testing.assert_allclose(pooled.cpu().numpy(), ref.numpy(), atol=3e-5, rtol=1e-4)
+    np.testing.assert_allclose(hid_out.cpu().numpy(), hn.numpy(), atol=3e-5, rtol=1e-5)
+
+
 def test_sgemm_l2norm_sim():
     g = torch.Generator().manual_seed(6)
     a, w, b = torch.randn(70, 768, generator=g), torch.randn(130, 768, generator=g), torch.randn(130, generator=g)
