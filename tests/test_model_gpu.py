@@ -277,6 +277,25 @@ def test_graph_replay_is_bit_equal_to_eager(synthetic_state_dict):
         assert torch.equal(at, r_at) and torch.equal(ta, r_ta)
     with pytest.raises(ValueError):
         g(w[:2], ids[:2], mask[:2])
+    # a larger eager call grows (frees + reallocates) the handle's workspaces, a re-pack frees the weight
+    # arena — the graph still points at the old memory.  The handle's generation counter makes the stale graph re-capture
+    # itself instead of replaying into freed memory.
+    import copy
+    m2 = copy.deepcopy(model)                                   # own handle: workspaces sized by the capture below
+    g2 = GraphedPairs(m2, 3, 80000, 16, max_patches=500)
+    assert g2.recaptures == 0
+    big = torch.from_numpy(W.make_waveforms(9, 8, 160000, "noise")).cuda()
+    gen = m2.generation()
+    m2.encode_audio(big, max_patches=500)                       # 8 x 500 rows > the 3 x 500 the graph was captured with
+    assert m2.generation() > gen
+    at, ta = g2(w, ids, mask)
+    assert g2.recaptures == 1
+    a, t = m2.encode_pairs(w, ids, mask, max_patches=500)
+    r_at, r_ta = m2.similarity(a, t)
+    assert torch.equal(at, r_at) and torch.equal(ta, r_ta)
+    m2.repack()
+    at, ta = g2(w, ids, mask)
+    assert g2.recaptures == 2 and torch.equal(at, r_at)
 
 
 def test_full_bench_size_properties(synthetic_state_dict):
