@@ -311,8 +311,8 @@ def run_ours(args):
             if world > 1:
                 return cdist.sharded_contrastive_logits(model, a, t)
             return model.similarity(a, t)
-        if world > 1:           # text embeddings gathered under the audio tower, audio embeddings after it
-            return cdist.sharded_pairs_logits(model, w, i, m, max_patches=MAX_PATCHES)
+        if world > 1 and not args.diag_local:   # text embeddings gathered under the audio tower, audio embeddings after it
+            return cdist.sharded_pairs_logits(model, w, i, m, max_patches=MAX_PATCHES, use_peer_memory=args.exchange == "peer")
         a, t = model.encode_pairs(w, i, m, max_patches=MAX_PATCHES)
         return model.similarity(a, t)
 
@@ -322,8 +322,27 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = step(wave_d, ids_d, mask_d)
+    # N > 1: the step as a software pipeline (dist.PipelinedPairs): step k's towers + publication, then the logits of step
+    # k - 1; K steps still produce K logits blocks inside the timed region (the last one by flush()).
+    pipe = None
+    if world > 1 and args.exchange == "peer" and not args.diag_local and not args.serial_towers and not args.no_pipeline:
+        try:
+            pipe = cdist.PipelinedPairs(model, B, MAX_PATCHES)
+        except RuntimeError as e:
+            sys.stderr.write(f"bench.py: {e}; plain per-step exchange\n")
+
+    def run_steps(k, w, i, m):
+        """k steps on resident inputs; returns the logits of the last one."""
+        if pipe is None:
+            o = None
+            for _ in range(k):
+                o = step(w, i, m)
+            return o
+        for _ in range(k):
+            pipe.step(w, i, m)
+        return pipe.flush()
+
+    out = run_steps(max(args.warmup, 3), wave_d, ids_d, mask_d)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ---------------------------------------------------------------
@@ -333,8 +352,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        out = step(wave_d, ids_d, mask_d)
+    out = run_steps(args.steps, wave_d, ids_d, mask_d)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -356,6 +374,19 @@ def run_ours(args):
     ms_serial = r0.elapsed_time(r1)
     clocks = sampler.stop()
 
+    if args.diag_local:
+        tt = torch.tensor([ms_total / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(tt) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, tt)
+        else:
+            allr = [tt]
+        if rank == 0:
+            print(json.dumps({"diag_local": True, "n_gpus": world, "per_rank_ms_per_step": [round(float(x), 3) for x in allr],
+                              "clocks_rank0": clocks}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": round(ms_total / args.steps, 3), "gpu_launches": int(launches)}))
@@ -380,9 +411,12 @@ def run_ours(args):
                 bufs[b][2].copy_(mask_h, non_blocking=True)
                 ready[b].record(copy_s)
             comp_s.wait_event(ready[b])
-            o = step(*bufs[b])
+            o = step(*bufs[b]) if pipe is None else pipe.step(*bufs[b])
             free[b].record(comp_s)
-            out_h[b].copy_(o[0], non_blocking=True)
+            if o is not None:
+                out_h[b].copy_(o[0], non_blocking=True)
+        if pipe is not None:
+            out_h[k & 1].copy_(pipe.flush()[0], non_blocking=True)
 
     e2e_loop(2)
     barrier()
@@ -399,7 +433,14 @@ def run_ours(args):
     a_fix = torch.nn.functional.normalize(torch.randn(B, 768, device=dev), dim=-1)
     t_fix = torch.nn.functional.normalize(torch.randn(B, 768, device=dev), dim=-1)
 
+    ex = cdist.peer_exchange(model, B) if (world > 1 and args.exchange == "peer") else None
+
     def tail():
+        if world > 1 and ex is not None:
+            ex.scatter(t_fix, ex.TEXT)
+            ex.scatter(a_fix, ex.AUDIO)
+            at_b, _ = model.similarity(ex.local_rows(ex.AUDIO), ex.gathered(ex.TEXT), want_ta=False)
+            return at_b, model.similarity(ex.local_rows(ex.TEXT), ex.gathered(ex.AUDIO), want_ta=False)[0]
         if world > 1:
             t_all = cdist.gather_embedding(t_fix, None, "text")
             at_b, _ = model.similarity(a_fix, t_all, want_ta=False)
@@ -498,9 +539,13 @@ def run_ours(args):
                         "ms_per_step": round(ms_e2e / args.steps, 3), "checksum": checksum},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
                 "gpu_library_baseline": lib_base,
-                "tail": {"ms": round(tail_ms, 4), "what": ("text gather + audio gather (NCCL all_gather_into_tensor, 0.79 MB per "
-                         "rank each) + two [B, N*B] similarity launches, timed alone; in the step the text gather is hidden under "
-                         "the audio tower") if world > 1 else "similarity kernel (both directions), timed alone"},
+                "tail": {"ms": round(tail_ms, 4), "what": (("exchange of both modalities' embeddings (" +
+                         ("L2-norm kernels storing into every peer's matrix over NVLink + flag waits" if ex is not None else
+                          "two NCCL all_gather_into_tensor, 0.79 MB per rank each") +
+                         ") + two [B, N*B] similarity launches, timed alone; in the step the text exchange is hidden under "
+                         "the audio tower") if world > 1 else "similarity kernel (both directions), timed alone"),
+                         "exchange": (None if world == 1 else "peer-memory" if ex is not None else "nccl"),
+                         "pipelined": pipe is not None},
                 "per_rank_ms_per_step": per_rank}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -655,6 +700,14 @@ def main():
                     help="pairs = BASELINE configs 3/4 (headline); zeroshot = config 5 (400 x 5 s clips, 50 prompts of 100 tokens)")
     ap.add_argument("--serial-towers", action="store_true", help="run the text tower after the audio tower on one stream")
     ap.add_argument("--profile", action="store_true", help="profiling run: resident-input region only (for ncu)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the embeddings are exchanged: peer = stores into peer memory fused into the L2-norm kernel "
+                         "(default; falls back to nccl when symmetric memory is unavailable), nccl = two all-gathers")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="N > 1: compute every step's logits inside the step (all ranks meet every step) instead of one step later")
+    ap.add_argument("--diag-local", action="store_true",
+                    help="diagnostic (N > 1): no exchange, every rank computes its local logits only and reports its own ms/step "
+                         "— separates GPU-to-GPU spread from the cost of the collective; not a bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

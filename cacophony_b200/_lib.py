@@ -54,6 +54,8 @@ SIGNATURES = {
     "caco_sgemm_nt": (_I, [_P, _I, _P, _I, _P, _F, _P, _I, _I, _I, _I, _P]),
     "caco_l2norm": (_I, [_P, _P, _I, _I, _F, _P]),
     "caco_sim_logits": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "caco_l2norm_scatter": (_I, [_P, _I, _I, _F, _P, C.c_longlong, C.c_longlong, _I, C.c_uint, _I, _P, _P]),
+    "caco_wait_flags": (_I, [_P, _I, C.c_uint, _I, _P, _P]),
     "caco_model_create": (_I, [C.POINTER(CacoConfig), C.POINTER(_P)]),
     "caco_model_destroy": (None, [_P]),
     "caco_model_set_tensor": (_I, [_P, C.c_char_p, _P, _L]),

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libcaco_b200.so")
-SOURCES = ["gemm.cu", "frontend.cu", "attention.cu", "attention_pp.cu", "rowops.cu", "evalops.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "frontend.cu", "attention.cu", "attention_pp.cu", "rowops.cu", "evalops.cu", "exchange.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -135,6 +135,20 @@ int caco_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float*
 /* ---- K7: e / ||e + 1e-10||_2 per row (caco.py:146,173). in == out allowed. */
 int caco_l2norm(const float* in, float* out, int rows, int dim, float eps, void* stream);
 
+/* ---- K7 fused with the path's one exchange: out-of-place L2 normalisation whose result rows are stored
+ * straight into every rank's gathered embedding matrix through NVLink peer mappings, then a release flag per peer.
+ * peer_base_dev: DEVICE array [world] of base pointers of the ranks' symmetric buffers (this rank's own included); the rows go
+ * to peer_base[p] + dst_byte_offset (the caller puts this rank's row block there), the flag to the uint32 array at
+ * peer_base[p] + flag_byte_offset, slot flag_index, value `epoch` (monotonically increasing per slot).  ticket: one zeroed
+ * device uint32 per concurrently used stream.  world <= 16. */
+int caco_l2norm_scatter(const float* in, int rows, int dim, float eps, void* const* peer_base_dev, long long dst_byte_offset,
+                        long long flag_byte_offset, int flag_index, unsigned int epoch, int world, unsigned int* ticket,
+                        void* stream);
+/* One-CTA kernel that returns once flags[0..n) >= epoch (acquire at system scope): what the similarity launch is ordered
+ * behind.  After timeout_ms (default 10 s) it gives up and writes 1 + the late slot to *status (DEVICE int, may be NULL)
+ * instead of hanging the GPU. */
+int caco_wait_flags(const unsigned int* flags, int n, unsigned int epoch, int timeout_ms, int* status, void* stream);
+
 /* ---- K8: at = exp(logit_scale)·A·Tᵀ, ta = atᵀ (caco.py:208-210).  A [na,dim], T [nt,dim] f32.
  * logit_scale is a DEVICE pointer to the scalar parameter.  ta may be NULL.                          */
 int caco_sim_logits(const float* a, const float* t, const float* logit_scale, float* at, float* ta, int na, int nt,

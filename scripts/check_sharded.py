@@ -22,14 +22,37 @@ wave, ids, mask = synth_inputs(B, 7)
 lo, hi = cdist.shard_range(B, rank, world)
 a, t = model.encode_pairs(wave[lo:hi].cuda(), ids[lo:hi].cuda(), mask[lo:hi].cuda(), max_patches=MAX_PATCHES)
 at_blk, ta_blk = cdist.sharded_contrastive_logits(model, a, t)
-torch.cuda.synchronize()
+# the whole sharded step with the text gather hidden under the audio tower: must equal the plain form bit for bit
 ok = True
+for peer in (False, True, True, True):          # NCCL exchange, then the peer-memory exchange three steps in a row (both parities)
+    at_blk2, ta_blk2 = cdist.sharded_pairs_logits(model, wave[lo:hi].cuda(), ids[lo:hi].cuda(), mask[lo:hi].cuda(),
+                                                  max_patches=MAX_PATCHES, use_peer_memory=peer)
+    torch.cuda.synchronize()
+    same = torch.equal(at_blk, at_blk2) and torch.equal(ta_blk, ta_blk2)
+    if not same:
+        print(f"rank {rank}: sharded_pairs_logits(use_peer_memory={peer}) differs from sharded_contrastive_logits: "
+              f"{(at_blk - at_blk2).abs().max().item():.3e} {(ta_blk - ta_blk2).abs().max().item():.3e}")
+    ok = ok and same
+ex = cdist.peer_exchange(model, hi - lo)
+if ex is not None:
+    # the software-pipelined form: logits come out one call later and must be the same blocks, bit for bit, over 6 steps
+    pipe = cdist.PipelinedPairs(model, hi - lo, MAX_PATCHES)
+    outs = [pipe.step(wave[lo:hi].cuda(), ids[lo:hi].cuda(), mask[lo:hi].cuda()) for _ in range(6)] + [pipe.flush()]
+    torch.cuda.synchronize()
+    same = outs[0] is None and all(torch.equal(o[0], at_blk) and torch.equal(o[1], ta_blk) for o in outs[1:])
+    if not same:
+        print(f"rank {rank}: PipelinedPairs differs from sharded_contrastive_logits")
+    ok = ok and same
+if rank == 0:
+    print("exchange:", "peer-memory stores fused into the L2-norm kernel" if ex is not None else "NCCL all-gather (peer memory unavailable)")
+if ex is not None:
+    ex.check()
 if rank == 0:
     a_all, t_all = model.encode_pairs(wave.cuda(), ids.cuda(), mask.cuda(), max_patches=MAX_PATCHES)
     at, ta = model.similarity(a_all, t_all)
     d1 = (at[lo:hi] - at_blk).abs().max().item()
     d2 = (ta[lo:hi] - ta_blk).abs().max().item()
-    ok = d1 < 1e-4 and d2 < 1e-4 and tuple(at_blk.shape) == (hi - lo, B)
+    ok = ok and d1 < 1e-4 and d2 < 1e-4 and tuple(at_blk.shape) == (hi - lo, B)
     print(f"sharded vs single-GPU: max|d at| = {d1:.2e}, max|d ta| = {d2:.2e}, block {tuple(at_blk.shape)} -> {'OK' if ok else 'FAIL'}")
 
 # ---- config #5 shape (scaled down): 5 s clips sharded, class prompts (T = 100) replicated, predictions gathered

@@ -1,5 +1,6 @@
 #!/bin/bash
-N=${1:-8}
+# N = 1 and N = 8 back to back on the same box (scaling is only meaningful on one box), + config 5 on 8 GPUs + sharded checks
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 scripts/check_sharded.py > gpurun_out/check_sharded_n$N.log 2>&1; echo "check_sharded rc=$?"; grep "sharded\|config-5" gpurun_out/check_sharded_n$N.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_n$N.json | cut -c1-220
+timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n1_samebox.json 2> gpurun_out/bench_n1_samebox.err; echo "bench n1 rc=$?"; tail -1 gpurun_out/bench_n1_samebox.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['e2e']['value'], d['clocks'])"
+bash scripts/gpu_n2.sh 8
