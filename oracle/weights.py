@@ -165,7 +165,8 @@ def make_state_dict(seed: int, sharp: float = 1.0, outlier: bool = False, **spec
     """Synthetic encoder-path ``state_dict`` as CPU fp32 torch tensors.  outlier: checkpoint-like outlier structure (LayerNorm
     gains x 30 in six channels, two residual channels at +-300, a few fc1 pre-activations near 1e3)."""
     import torch
-    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in iter_weights(seed, sharp, outlier, **spec_kw)}
+    return {k: torch.from_numpy(np.array(v, dtype=np.float32, copy=True, order="C"))          # keeps logit_scale 0-d
+            for k, v in iter_weights(seed, sharp, outlier, **spec_kw)}
 
 
 # ---------------------------------------------------------------------------------------------
