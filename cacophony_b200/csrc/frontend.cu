@@ -2,16 +2,20 @@
 // Replaces compute_mel_spectrogram + spectrogram_to_patches + prepare_audio_batch
 // (src/eval/eval_caco_torch.py:41-105, :108-151, :181-206), batched and without the host numpy hop.
 //
-// One CTA per (clip, 16-frame group) = one patch row t: it stages the 2912 samples the 16 frames touch and the constant
-// tables with cp.async, runs 16 real 512-point FFTs (each a 256-point complex FFT done as two radix-16 passes in the
+// One CTA per (clip, 16-frame group) = one patch row t: it stages the 2912 samples the 16 frames touch with TMA (twelve
+// 256-sample tiles of a 2-D tensor map over wave[batch][samples]; samples past the clip's end are zero-filled by the
+// hardware, which IS the reference's tail padding) and the 9.3 KB of constant tables with one bulk copy, all completing on
+// one mbarrier; unaligned or ragged-with-garbage inputs take a cp.async path.  Then 16 real 512-point FFTs (each a 256-point complex FFT done as two radix-16 passes in the
 // registers of 16 threads, one padded shared-memory exchange between them, fp32, host-computed twiddles) + real split,
 // applies the sparse HTK filterbank (505 non-zeros), log(x+1e-5)*0.2+0.9, and writes the 8 patches of that row — 8 KB
 // contiguous in the [B, max_patches, 256] layout — with coalesced 128-byte stores.  Algorithmic HBM traffic: 1.158 MB per
 // 10 s clip.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
 
@@ -120,6 +124,19 @@ __device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// single-instruction MUFU forms: sqrt.approx and lg2.approx are accurate to ~1 ulp / 2^-22 absolute, three orders of magnitude
+// inside the log-mel tolerance (tests/util.py), and save ~17 instructions per magnitude / log over sqrtf / logf — the kernel is
+// instruction-issue-bound (profiles/r02_notes.md)
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ln(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.69314718055994530942f;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -165,10 +182,20 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 
 constexpr int FE_ZLD = 17;                               // padded row of the 16x16 exchange buffer (float2 units)
 constexpr int FE_ZFRAME = 16 * FE_ZLD;                   // 272 float2 per frame (>= 257 floats for the magnitudes)
-constexpr int FE_OFF_Z = FE_SAMPLES * 4;                                   // 11648 (16-byte aligned)
+constexpr int FE_TMA_BOX = 256;                          // samples per TMA tile (the box limit of a tensor-map dimension)
+constexpr int FE_TMA_TILES = (FE_SAMPLES + FE_TMA_BOX - 1) / FE_TMA_BOX;   // 12 tiles = 3072 samples staged (2912 used)
+constexpr int FE_OFF_Z = FE_TMA_TILES * FE_TMA_BOX * 4;                    // 12288 (128-byte aligned: TMA destination)
 constexpr int FE_OFF_TAB = FE_OFF_Z + FE_FRAMES * FE_ZFRAME * 8;           // 46464
-constexpr int FE_SMEM_BYTES = FE_OFF_TAB + (int)sizeof(FeTables);          // 55.7 KB -> four CTAs per SM
-static_assert(FE_OFF_Z % 16 == 0 && FE_OFF_TAB % 16 == 0, "cp.async destinations must be 16-byte aligned");
+constexpr int FE_OFF_MBAR = FE_OFF_TAB + (int)sizeof(FeTables);
+constexpr int FE_SMEM_BYTES = FE_OFF_MBAR + 16;                            // 56.4 KB -> four CTAs per SM
+static_assert(FE_OFF_Z % 128 == 0 && FE_OFF_TAB % 16 == 0 && FE_OFF_MBAR % 8 == 0, "TMA / cp.async / mbarrier alignment");
+
+// 1-D bulk copy global -> shared, completing on an mbarrier (the constant tables)
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 // 16 threads per frame, 16 frames per CTA.  The 512-point real FFT of a frame is a 256-point complex FFT of
 // z[n] = x[2n] + i x[2n+1], done as 16 x 16: thread n2 transforms z[16 n1 + n2] over n1 in registers, multiplies by
@@ -176,11 +203,15 @@ static_assert(FE_OFF_Z % 16 == 0 && FE_OFF_TAB % 16 == 0, "cp.async destinations
 // over n2 and owns X[k1 + 16 k2]; the conjugate partner Z[256 - k] for the real split comes from a second pass through the
 // same tile.  Two shared-memory round trips per frame instead of the eight of a radix-4 Stockham, and only warp-level
 // synchronisation (a frame lives in half a warp).
+// USE_TMA: samples staged by tensor-map tile loads (needs a 16-byte aligned base and row pitch); MASK_TAIL: samples past a
+// ragged clip's own length are forced to zero at the window stage (the tensor map only knows the common row length).
+template <bool USE_TMA, bool MASK_TAIL>
 __global__ void __launch_bounds__(256)
-frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths, int stride, int n_samples_u, int max_patches,
-                float* __restrict__ patches, __half* __restrict__ patches_f16, float* __restrict__ time_inds,
-                float* __restrict__ freq_inds, float* __restrict__ mask, float* __restrict__ log_mel) {
-  extern __shared__ __align__(16) uint8_t fe_smem[];
+frontend_kernel(const __grid_constant__ CUtensorMap map_wave, const float* __restrict__ wave, const int* __restrict__ lengths,
+                int stride, int n_samples_u, int max_patches, float* __restrict__ patches, __half* __restrict__ patches_f16,
+                float* __restrict__ time_inds, float* __restrict__ freq_inds, float* __restrict__ mask,
+                float* __restrict__ log_mel) {
+  extern __shared__ __align__(128) uint8_t fe_smem[];
   float* s_x = reinterpret_cast<float*>(fe_smem);                                   // 2912 samples; later the log-mel tile
   float2* s_z = reinterpret_cast<float2*>(fe_smem + FE_OFF_Z);                      // [16 frames][16][17]
   const FeTables& tab = *reinterpret_cast<const FeTables*>(fe_smem + FE_OFF_TAB);
@@ -227,9 +258,25 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     return;
   }
 
-  // ---- stage the tables and the samples (zero tail pad, eval_caco_torch.py:72-78) with cp.async: every copy of the CTA is
-  // in flight at once instead of one exposed global-load latency per loop trip
-  {
+  // ---- stage the tables and the samples (zero tail pad, eval_caco_torch.py:72-78)
+  if constexpr (USE_TMA) {
+    // one thread: 12 tile loads of 256 samples (coordinates past the row's end are zero-filled by the TMA unit) + one bulk
+    // copy of the tables, 21.6 KB in flight on one mbarrier; nobody else issues a load instruction
+    const uint32_t bar = smem_u32(fe_smem + FE_OFF_MBAR);
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(bar, FE_TMA_TILES * FE_TMA_BOX * 4 + (uint32_t)sizeof(FeTables));
+      bulk_copy_g2s(smem_u32(fe_smem + FE_OFF_TAB), &g_fe, (uint32_t)sizeof(FeTables), bar);
+      const int s0 = frame0 * FE_HOP;
+#pragma unroll
+      for (int i = 0; i < FE_TMA_TILES; ++i)
+        tma_load_2d(smem_u32(fe_smem) + i * FE_TMA_BOX * 4, &map_wave, bar, s0 + i * FE_TMA_BOX, b);
+    }
+    __syncthreads();                      // the barrier's init is visible to every waiter
+    mbar_wait(bar, 0);
+  } else {
+    // cp.async: every copy of the CTA is in flight at once instead of one exposed global-load latency per loop trip
     const uint8_t* src = reinterpret_cast<const uint8_t*>(&g_fe);
     uint8_t* dst = fe_smem + FE_OFF_TAB;
     for (int i = tid; i < (int)sizeof(FeTables) / 16; i += 256) cp_async16(dst + 16 * i, src + 16 * i);
@@ -246,8 +293,8 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
       }
     }
     cp_async_wait_all();
+    __syncthreads();
   }
-  __syncthreads();
 
   const int fr = tid >> 4;       // frame within the CTA
   const int q = tid & 15;        // n2 in pass 1, k1 in pass 2
@@ -261,7 +308,12 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
       const int i0 = 2 * (16 * n1 + q), i1 = i0 + 1;
       const float w0 = (i0 >= FE_WOFF && i0 < FE_WOFF + FE_WIN) ? tab.win[i0 - FE_WOFF] : 0.0f;
       const float w1 = (i1 >= FE_WOFF && i1 < FE_WOFF + FE_WIN) ? tab.win[i1 - FE_WOFF] : 0.0f;
-      const float2 xx = *reinterpret_cast<const float2*>(xf + i0);
+      float2 xx = *reinterpret_cast<const float2*>(xf + i0);
+      if constexpr (MASK_TAIL) {           // ragged clip shorter than the staged row: its tail is zero, whatever the buffer holds
+        const int g0 = (frame0 + fr) * FE_HOP + i0;
+        if (g0 >= n_samples) xx.x = 0.0f;
+        if (g0 + 1 >= n_samples) xx.y = 0.0f;
+      }
       v[n1] = make_float2(xx.x * w0, xx.y * w1);
     }
   }
@@ -293,10 +345,10 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     const float2 w = tab.w512[k];
     const float xr = er + (w.x * orr - w.y * oi);
     const float xi = ei + (w.x * oi + w.y * orr);
-    mag[k2] = sqrtf(xr * xr + xi * xi);
+    mag[k2] = fast_sqrt(xr * xr + xi * xi);
     if (k == 0) {                                           // X[256] = E - O at k = 0 (W512^256 = -1)
       const float nr = er - orr, ni = ei - oi;
-      mag_nyq = sqrtf(nr * nr + ni * ni);
+      mag_nyq = fast_sqrt(nr * nr + ni * ni);
     }
   }
   __syncwarp();                                             // every partner read is done: the tile becomes the magnitudes
@@ -313,7 +365,7 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
     const float* mw = tab.mel_w + tab.mel_woff[m];
     float acc = 0.0f;
     for (int c = 0; c < cnt; ++c) acc = fmaf(s_mag[st + c], mw[c], acc);
-    s_out[fr][m] = logf(acc + 1e-5f) * 0.2f + 0.9f;
+    s_out[fr][m] = fast_ln(acc + 1e-5f) * 0.2f + 0.9f;
   }
   __syncthreads();
   // ---- optional raw log-mel [B, n_frames, 128]
@@ -347,6 +399,27 @@ frontend_kernel(const float* __restrict__ wave, const int* __restrict__ lengths,
   }
 }
 
+// 2-D tensor map over wave[batch][n_samples] fp32, box = 256 samples of one clip, no swizzle, zero fill out of bounds
+static int make_tmap_wave(CUtensorMap* map, const float* wave, int batch, int n_samples) {
+  typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return CACO_ERR_DRIVER;
+    enc = reinterpret_cast<PFN>(p);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)n_samples, (cuuint64_t)batch};
+  cuuint64_t strides[1] = {(cuuint64_t)n_samples * 4};
+  cuuint32_t box[2] = {FE_TMA_BOX, 1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wave), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : CACO_ERR_DRIVER;
+}
+
 int frontend(const float* wave, const int* lengths, int batch, int n_samples, int max_patches, float* patches,
              void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream) {
   if (!wave || (!patches && !patches_f16) || !time_inds || !freq_inds || !mask || batch <= 0 || n_samples <= 0 || max_patches <= 0)
@@ -361,12 +434,28 @@ int frontend(const float* wave, const int* lengths, int batch, int n_samples, in
   dim3 grid(gx, batch);
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(frontend_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
+    if (!e) e = cudaFuncSetAttribute(frontend_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
+    if (!e) e = cudaFuncSetAttribute(frontend_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FE_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_once.done();
   }
-  frontend_kernel<<<grid, 256, FE_SMEM_BYTES, stream>>>(wave, lengths, n_samples, n_samples, max_patches, patches,
-                                            reinterpret_cast<__half*>(patches_f16), time_inds, freq_inds, mask, log_mel);
+  // TMA staging needs a 16-byte aligned base and row pitch (every real batch: torch allocations, 160000-sample rows); the
+  // tensor map's inner extent is the common row length, so OOB zero fill reproduces the reference's tail padding
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  bool use_tma = ((reinterpret_cast<uintptr_t>(wave) & 15) == 0) && ((n_samples & 3) == 0) && batch <= 65535;
+  if (use_tma) use_tma = make_tmap_wave(&map, wave, batch, n_samples) == 0;
+  __half* p16 = reinterpret_cast<__half*>(patches_f16);
+  if (use_tma && lengths == nullptr)
+    frontend_kernel<true, false><<<grid, 256, FE_SMEM_BYTES, stream>>>(map, wave, lengths, n_samples, n_samples, max_patches, patches,
+                                                                       p16, time_inds, freq_inds, mask, log_mel);
+  else if (use_tma)
+    frontend_kernel<true, true><<<grid, 256, FE_SMEM_BYTES, stream>>>(map, wave, lengths, n_samples, n_samples, max_patches, patches,
+                                                                      p16, time_inds, freq_inds, mask, log_mel);
+  else
+    frontend_kernel<false, false><<<grid, 256, FE_SMEM_BYTES, stream>>>(map, wave, lengths, n_samples, n_samples, max_patches, patches,
+                                                                        p16, time_inds, freq_inds, mask, log_mel);
   count_launch();
   return (int)cudaGetLastError();
 }
