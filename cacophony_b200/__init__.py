@@ -9,7 +9,8 @@ from .checkpoint import convert_caco_checkpoint
 from .frontend import DatasetConfig, compute_mel_spectrogram, spectrogram_to_patches, prepare_audio_batch
 from .loader import pad_ragged, prepare_audio_batch_ragged, resample_to_16k, load_audio
 from .eval import (load_caco_torch, prepare_text_batch, compute_audio_embedding, compute_text_embedding,
-                   compute_all_class_embeddings, zs_classification, audio_retrieval, compute_retrieval_metric)
+                   compute_all_class_embeddings, zs_classification, audio_retrieval, compute_retrieval_metric,
+                   decode_caption, decode_caption_ids)
 
 __all__ = [
     "CACO", "CACOConfig", "AudioAttentionPooler", "create_caco_model", "convert_caco_checkpoint",
@@ -17,5 +18,5 @@ __all__ = [
     "RobertaModel", "RobertaConfig", "RobertaDecoder", "NORM_EPS", "DatasetConfig", "compute_mel_spectrogram", "spectrogram_to_patches",
     "prepare_audio_batch", "pad_ragged", "prepare_audio_batch_ragged", "resample_to_16k", "load_audio", "load_caco_torch",
     "prepare_text_batch", "compute_audio_embedding", "compute_text_embedding", "compute_all_class_embeddings",
-    "zs_classification", "audio_retrieval", "compute_retrieval_metric",
+    "zs_classification", "audio_retrieval", "compute_retrieval_metric", "decode_caption", "decode_caption_ids",
 ]

@@ -64,6 +64,9 @@ SIGNATURES = {
     "caco_model_generation": (C.c_uint64, [_P]),
     "caco_model_audio_embedding": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_text_embedding": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "caco_model_decoder_logits": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "caco_model_decoder_vocab": (_I, [_P]),
+    "caco_attention_cross": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "caco_model_encode_audio": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "caco_model_encode_audio_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "caco_model_logit_scale": (_P, [_P]),

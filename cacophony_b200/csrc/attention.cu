@@ -69,10 +69,13 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const __half* src, int r
   }
 }
 
+// q / k / v may come from different buffers and sequences (cross-attention of the captioning decoder, roberta.py:76-83,
+// 205-211: queries = text tokens, keys / values = audio tokens): Sq query rows with row pitch ldq, Skv key rows with pitch ldkv;
+// self-attention passes the three column blocks of one packed qkv buffer.  mask is per KEY ([batch, Skv], 1 = keep).
 template <int DH, bool CAUSAL = false>
 __global__ void __launch_bounds__(128)
-attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__ mask, __half* __restrict__ out, int S,
-                       int H, float scale_log2) {
+attention_audio_kernel(const __half* __restrict__ q_ptr, int ldq, const __half* __restrict__ k_ptr, const __half* __restrict__ v_ptr,
+                       int ldkv, const float* __restrict__ mask, __half* __restrict__ out, int Sq, int S, int H, float scale_log2) {
   using Cfg = AttnCfg<DH>;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
@@ -83,16 +86,15 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * AT_BM, h = blockIdx.y, b = blockIdx.z;
   const int D = H * DH;
-  const int ld = 3 * D;
-  const __half* base = qkv + (size_t)b * S * ld;
-  const __half* gQ = base + h * DH;
-  const __half* gK = base + D + h * DH;
-  const __half* gV = base + 2 * D + h * DH;
+  const int ld = ldkv;
+  const __half* gQ = q_ptr + (size_t)b * Sq * ldq + h * DH;
+  const __half* gK = k_ptr + (size_t)b * S * ldkv + h * DH;
+  const __half* gV = v_ptr + (size_t)b * S * ldkv + h * DH;
   const float* gmask = mask + (size_t)b * S;
 
   // causal (text tower, roberta.py:297-310): key tiles past this query tile's last row are never needed
   const int n_tiles = CAUSAL ? min((S + AT_BN - 1) / AT_BN, (q0 + AT_BM - 1) / AT_BN + 1) : (S + AT_BN - 1) / AT_BN;
-  load_tile<DH>(sQ, gQ, q0, S, ld, tid);
+  load_tile<DH>(sQ, gQ, q0, Sq, ldq, tid);
   load_tile<DH>(sK, gK, 0, S, ld, tid);
   load_tile<DH>(sV, gV, 0, S, ld, tid);
   if (tid < AT_BN) sBias[tid] = (tid < S && gmask[tid] != 0.0f) ? 0.0f : -INFINITY;
@@ -235,10 +237,10 @@ attention_audio_kernel(const __half* __restrict__ qkv, const float* __restrict__
   }
   __syncthreads();
   constexpr int CH = DH / 8;
-  __half* gO = out + (size_t)b * S * D + h * DH;
+  __half* gO = out + (size_t)b * Sq * D + h * DH;
   for (int i = tid; i < AT_BM * CH; i += 128) {
     const int r = i / CH, c = i % CH;
-    if (q0 + r < S) *reinterpret_cast<uint4*>(gO + (size_t)(q0 + r) * D + c * 8) = *reinterpret_cast<const uint4*>(sO + r * Cfg::LD + c * 8);
+    if (q0 + r < Sq) *reinterpret_cast<uint4*>(gO + (size_t)(q0 + r) * D + c * 8) = *reinterpret_cast<const uint4*>(sO + r * Cfg::LD + c * 8);
   }
 }
 
@@ -259,11 +261,15 @@ int attention_audio(const void* qkv, const float* mask, void* out, int batch, in
   if (dh == 96) {
     static PerDeviceOnce set96;
     if (set96.first()) { e = cudaFuncSetAttribute(attention_audio_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<96>::SMEM_BYTES); if (e) return (int)e; set96.done(); }
-    attention_audio_kernel<96><<<grid, 128, AttnCfg<96>::SMEM_BYTES, stream>>>((const __half*)qkv, mask, (__half*)out, seq, heads, scale_log2);
+    const __half* p = (const __half*)qkv;
+    const int D = heads * dh;
+    attention_audio_kernel<96><<<grid, 128, AttnCfg<96>::SMEM_BYTES, stream>>>(p, 3 * D, p + D, p + 2 * D, 3 * D, mask, (__half*)out, seq, seq, heads, scale_log2);
   } else if (dh == 64) {
     static PerDeviceOnce set64;
     if (set64.first()) { e = cudaFuncSetAttribute(attention_audio_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES); if (e) return (int)e; set64.done(); }
-    attention_audio_kernel<64><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>((const __half*)qkv, mask, (__half*)out, seq, heads, scale_log2);
+    const __half* p = (const __half*)qkv;
+    const int D = heads * dh;
+    attention_audio_kernel<64><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>(p, 3 * D, p + D, p + 2 * D, 3 * D, mask, (__half*)out, seq, seq, heads, scale_log2);
   } else {
     return CACO_ERR_ARG;
   }
@@ -286,8 +292,33 @@ int attention_text(const void* qkv, const float* key_mask, void* out, int batch,
     attr.done();
   }
   dim3 grid((T + AT_BM - 1) / AT_BM, heads, batch);
+  const __half* p = (const __half*)qkv;
+  const int D = heads * dh;
   attention_audio_kernel<64, true><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>(
-      (const __half*)qkv, key_mask, (__half*)out, T, heads, (1.0f / sqrtf((float)dh)) * 1.4426950408889634f);
+      p, 3 * D, p + D, p + 2 * D, 3 * D, key_mask, (__half*)out, T, T, heads, (1.0f / sqrtf((float)dh)) * 1.4426950408889634f);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-attention of the captioning decoder (roberta.py:76-102 with key_value_states, mask :358-361): queries from the text
+// side ([batch*Tq, heads*64], row pitch ldq), keys | values from the audio side (one [batch*Skv, 2*heads*64] buffer: k | v)
+// ------------------------------------------------------------------------------------------------
+int attention_cross(const void* q, int ldq, const void* kv, const float* key_mask, void* out, int batch, int Tq, int Skv, int heads,
+                    int dh, cudaStream_t stream) {
+  if (!q || !kv || !key_mask || !out || batch <= 0 || Tq <= 0 || Skv <= 0 || heads <= 0 || dh != 64) return CACO_ERR_ARG;
+  const int D = heads * dh;
+  if ((ldq & 7) || (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(kv) & 15)) return CACO_ERR_ALIGN;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    cudaError_t e = cudaFuncSetAttribute(attention_audio_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::SMEM_BYTES);
+    if (e) return (int)e;
+    attr.done();
+  }
+  dim3 grid((Tq + AT_BM - 1) / AT_BM, heads, batch);
+  const __half* k = (const __half*)kv;
+  attention_audio_kernel<64, false><<<grid, 128, AttnCfg<64>::SMEM_BYTES, stream>>>(
+      (const __half*)q, ldq, k, k + D, 2 * D, key_mask, (__half*)out, Tq, Skv, heads, (1.0f / sqrtf((float)dh)) * 1.4426950408889634f);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -297,6 +328,10 @@ int attention_text(const void* qkv, const float* key_mask, void* out, int batch,
 extern "C" int caco_attention_audio(const void* qkv, const float* mask, void* out, int batch, int seq, int heads, int dh,
                                     void* stream) {
   return caco::attention_audio(qkv, mask, out, batch, seq, heads, dh, (cudaStream_t)stream);
+}
+extern "C" int caco_attention_cross(const void* q, int ldq, const void* kv, const float* key_mask, void* out, int batch, int Tq,
+                                    int Skv, int heads, int dh, void* stream) {
+  return caco::attention_cross(q, ldq, kv, key_mask, out, batch, Tq, Skv, heads, dh, (cudaStream_t)stream);
 }
 extern "C" int caco_attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
                                    void* stream) {

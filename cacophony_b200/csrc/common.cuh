@@ -82,6 +82,8 @@ int attention_audio(const void* qkv, const float* mask, void* out, int batch, in
                     cudaStream_t stream);
 int attention_text(const void* qkv, const float* key_mask, void* out, int batch, int T, int heads, int dh,
                    cudaStream_t stream);
+int attention_cross(const void* q, int ldq, const void* kv, const float* key_mask, void* out, int batch, int Tq, int Skv,
+                    int heads, int dh, cudaStream_t stream);
 int text_embed_ln(const int64_t* ids, const int64_t* position_ids, const float* word, const float* pos,
                   const float* type0, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16,
                   int batch, int T, int dim, int vocab, int max_pos, cudaStream_t stream);

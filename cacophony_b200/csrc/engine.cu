@@ -38,8 +38,17 @@ struct caco_model {
     const __half *qkv_w, *o_w, *fc1_w, *fc2_w;
     const float *qkv_b, *o_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   };
+  struct DLayer {          // captioning decoder layer (roberta.py:181-215 with crossattention): self-attention block as in TLayer,
+    TLayer self_ffn;       // + cross-attention: q from the text side, k | v (stacked [2D, D]) from the audio hidden state
+    const __half *cq_w, *ckv_w, *co_w;
+    const float *cq_b, *ckv_b, *co_b, *lnc_g, *lnc_b;
+  };
   std::vector<ALayer> al;
   std::vector<TLayer> tl;
+  std::vector<DLayer> dl;
+  const __half* dproj_w = nullptr;       // decoder_proj [vocab_pad, D] (rows past the vocabulary are zero)
+  float* dproj_b = nullptr;              // [vocab_pad] in arena32
+  int dec_vocab = 0, dec_vocab_pad = 0;
   const __half* in_w = nullptr;
   const float *in_b = nullptr, *freq_emb = nullptr, *an_g = nullptr, *an_b = nullptr;
   const float *ap_vw = nullptr, *ap_vb = nullptr, *ap_ow = nullptr, *ap_ob = nullptr;   // audio pooler value rows / out_proj
@@ -51,8 +60,8 @@ struct caco_model {
   float* arena32 = nullptr;    // packed text qkv biases + folded pooler vectors
   float *a_u = nullptr, *a_c = nullptr, *t_u = nullptr, *t_c = nullptr;
 
-  void* ws[2] = {nullptr, nullptr};      // [0] audio tower, [1] text tower: the towers may run on different streams
-  size_t ws_bytes[2] = {0, 0};
+  void* ws[3] = {nullptr, nullptr, nullptr};   // [0] audio tower, [1] text tower (they may run on different streams), [2] decoder
+  size_t ws_bytes[3] = {0, 0, 0};
   int device = -1;                       // the device the arenas / workspaces live on (a handle follows its model's .to())
   int packed_split = 0;                  // layout of arena16: 0 = [N, K] fp16, 1 = [N, 2K] fp16 hi | lo (split_weights)
   uint64_t generation = 0;               // bumped whenever a pointer a captured CUDA graph may have baked in is released
@@ -103,13 +112,28 @@ static int pack(caco_model* m, cudaStream_t st) {
   // ---- sizes
   const int split = m->opt.split_weights ? 1 : 0;
   const int64_t per_layer = 3 * D * D + D * D + 2 * F * D;
-  const int64_t n16 = (P * D + per_layer * (c.audio_layers + c.text_layers)) * (split ? 2 : 1);
-  const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * D + 4 * 64;
+  // captioning head (optional): present iff decoder_module.decoder_proj.weight was registered
+  int dec_layers = 0;
+  int64_t dec_vocab = 0, dec_vocab_pad = 0;
+  {
+    auto it = m->w.find("decoder_module.decoder_proj.weight");
+    if (it != m->w.end()) {
+      dec_vocab = it->second.n / D;
+      dec_vocab_pad = (dec_vocab + 7) & ~(int64_t)7;
+      while (m->w.count("decoder_module.encoder.layers." + std::to_string(dec_layers) + ".intermediate.dense.weight")) ++dec_layers;
+    }
+  }
+  const int64_t dec_per_layer = per_layer + D * D + 2 * D * D + D * D;      // + cross q, k | v, out
+  const int64_t n16 = (P * D + per_layer * (c.audio_layers + c.text_layers) + dec_per_layer * dec_layers + dec_vocab_pad * D) *
+                      (split ? 2 : 1);
+  const int64_t n32 = (int64_t)c.text_layers * 3 * D + (int64_t)(c.pool_heads + 1) * D + 4 * 64 +
+                      (int64_t)dec_layers * 6 * D + dec_vocab_pad;
   int cur = 0;
   cudaGetDevice(&cur);
   if (m->device != cur) {                // first pack, or the model moved to another GPU: nothing of the old device is kept
     free_ws(m, 0);
     free_ws(m, 1);
+    free_ws(m, 2);
     m->device = cur;
   }
   m->packed = false;
@@ -223,6 +247,70 @@ static int pack(caco_model* m, cudaStream_t st) {
     m->t_u = p32; p32 += D;
     m->t_c = p32; p32 += 64;
     CK(fold_query(query, kw, kb, 1.0f / sqrtf((float)D), m->t_u, m->t_c, 1, (int)D, (int)D, st));   // roberta.py:259
+  }
+  // ---- captioning decoder (roberta.py:329-373), only when its tensors were registered
+  m->dl.clear();
+  m->dl.resize(dec_layers);
+  m->dec_vocab = (int)dec_vocab;
+  m->dec_vocab_pad = (int)dec_vocab_pad;
+  for (int i = 0; i < dec_layers && rc == 0; ++i) {
+    const std::string L = "decoder_module.encoder.layers." + std::to_string(i) + ".";
+    caco_model::DLayer& d = m->dl[i];
+    caco_model::TLayer& l = d.self_ffn;
+    auto stack = [&](const std::string& blk, const char* const* names, int n, const __half** w_out, const float** b_out) {
+      __half* w0 = p16;
+      float* b0 = p32;
+      for (int j = 0; j < n; ++j) {
+        take16(need(m, L + blk + ".self." + names[j] + ".weight", D * D, &rc), D * D, D);
+        const float* b = need(m, L + blk + ".self." + names[j] + ".bias", D, &rc);
+        if (rc) return;
+        if (cudaMemcpyAsync(p32, b, D * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = CACO_ERR_STATE; return; }
+        p32 += D;
+      }
+      *w_out = w0;
+      *b_out = b0;
+    };
+    const char* qkv_n[3] = {"query", "key", "value"};
+    const char* q_n[1] = {"query"};
+    const char* kv_n[2] = {"key", "value"};
+    stack("attention", qkv_n, 3, &l.qkv_w, &l.qkv_b);
+    if (rc) return rc;
+    l.o_w = take16(need(m, L + "attention.output.dense.weight", D * D, &rc), D * D, D);
+    l.o_b = need(m, L + "attention.output.dense.bias", D, &rc);
+    l.ln1_g = need(m, L + "attention.output.LayerNorm.weight", D, &rc);
+    l.ln1_b = need(m, L + "attention.output.LayerNorm.bias", D, &rc);
+    stack("crossattention", q_n, 1, &d.cq_w, &d.cq_b);
+    stack("crossattention", kv_n, 2, &d.ckv_w, &d.ckv_b);
+    if (rc) return rc;
+    d.co_w = take16(need(m, L + "crossattention.output.dense.weight", D * D, &rc), D * D, D);
+    d.co_b = need(m, L + "crossattention.output.dense.bias", D, &rc);
+    d.lnc_g = need(m, L + "crossattention.output.LayerNorm.weight", D, &rc);
+    d.lnc_b = need(m, L + "crossattention.output.LayerNorm.bias", D, &rc);
+    l.fc1_w = take16(need(m, L + "intermediate.dense.weight", F * D, &rc), F * D, D);
+    l.fc1_b = need(m, L + "intermediate.dense.bias", F, &rc);
+    l.fc2_w = take16(need(m, L + "output.dense.weight", D * F, &rc), D * F, F);
+    l.fc2_b = need(m, L + "output.dense.bias", D, &rc);
+    l.ln2_g = need(m, L + "output.LayerNorm.weight", D, &rc);
+    l.ln2_b = need(m, L + "output.LayerNorm.bias", D, &rc);
+  }
+  if (rc) return rc;
+  m->dproj_w = nullptr;
+  if (dec_layers > 0) {
+    // vocabulary projection, rows padded to a multiple of 8 (50265 -> 50272) with zeros so that the GEMM's 16-byte stores apply
+    __half* w0 = p16;
+    const int64_t el = split ? 2 : 1;
+    e = cudaMemsetAsync(w0, 0, dec_vocab_pad * D * el * sizeof(__half), st);
+    if (e) return (int)e;
+    take16(need(m, "decoder_module.decoder_proj.weight", dec_vocab * D, &rc), dec_vocab * D, D);
+    p16 = w0 + dec_vocab_pad * D * el;
+    const float* pb = need(m, "decoder_module.decoder_proj.bias", dec_vocab, &rc);
+    if (rc) return rc;
+    m->dproj_b = p32;
+    e = cudaMemsetAsync(p32, 0, dec_vocab_pad * sizeof(float), st);
+    if (!e) e = cudaMemcpyAsync(p32, pb, dec_vocab * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e) return (int)e;
+    p32 += dec_vocab_pad;
+    m->dproj_w = w0;
   }
   m->packed = true;
   m->packed_split = split;
@@ -379,9 +467,73 @@ static int text_embedding(caco_model* m, const int64_t* ids, const float* mask, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------- captioning decoder
+// CACO.get_decoder_logits minus the text tower (caco.py:214-240 -> RobertaDecoder.forward, roberta.py:337-373): per layer
+// causal self-attention over the text hidden state, cross-attention to the audio hidden state (audio key mask), GELU MLP, all
+// post-LN; then the vocabulary projection.  text_hidden [B,T,D] f32 is the text tower's final hidden state, audio_hidden
+// [B,S,D] f32 the audio tower's LayerNorm-ed output.  logits_out [B,T,vocab] f32.
+static int decoder_logits(caco_model* m, const float* text_hidden, const float* text_mask, const float* audio_hidden,
+                          const float* audio_mask, int B, int T, int S, float* logits_out, cudaStream_t st) {
+  CK(ready(m, st));
+  OptionsScope scope(&m->opt);
+  if (m->dl.empty() || !m->dproj_w) { set_err("decoder_module tensors were not registered%s", ""); return CACO_ERR_STATE; }
+  if (!text_hidden || !text_mask || !audio_hidden || !audio_mask || !logits_out || B <= 0 || T <= 0 || S <= 0) return CACO_ERR_ARG;
+  const caco_config& c = m->cfg;
+  const int D = c.hidden, F = c.ffn, V = m->dec_vocab, Vp = m->dec_vocab_pad;
+  const size_t R = (size_t)B * T, RA = (size_t)B * S;
+  if (R > (1u << 20) || RA > (1u << 22)) return CACO_ERR_ARG;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const size_t o_x = carve(R * D * 4), o_x16 = carve(R * D * 2), o_a = carve(R * D * 4), o_a16 = carve(R * D * 2);
+  const size_t o_c = carve(R * D * 4), o_c16 = carve(R * D * 2), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2);
+  const size_t o_q = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2), o_ah = carve(RA * D * 2), o_kv = carve(RA * 2 * D * 2);
+  const size_t o_log = carve(R * (size_t)Vp * 4);
+  CK(ensure_ws(m, 2, off));
+  uint8_t* w = (uint8_t*)m->ws[2];
+  float *x = (float*)(w + o_x), *a = (float*)(w + o_a), *cc = (float*)(w + o_c), *logp = (float*)(w + o_log);
+  __half *x16 = (__half*)(w + o_x16), *a16 = (__half*)(w + o_a16), *c16 = (__half*)(w + o_c16), *qkv = (__half*)(w + o_qkv);
+  __half *att = (__half*)(w + o_att), *q = (__half*)(w + o_q), *mlp = (__half*)(w + o_mlp), *ah16 = (__half*)(w + o_ah);
+  __half* kv = (__half*)(w + o_kv);
+  const int Ri = (int)R, RAi = (int)RA;
+  cudaError_t e = cudaMemcpyAsync(x, text_hidden, R * D * 4, cudaMemcpyDeviceToDevice, st);
+  if (e) return (int)e;
+  CK(cast_f32_f16(text_hidden, x16, (int64_t)R * D, st));
+  CK(cast_f32_f16(audio_hidden, ah16, (int64_t)RA * D, st));
+  for (size_t i = 0; i < m->dl.size(); ++i) {
+    const caco_model::DLayer& d = m->dl[i];
+    const caco_model::TLayer& l = d.self_ffn;
+    // self-attention block (causal + text padding, roberta.py:346-355)
+    CK(lin(m, x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, Ri, 3 * D, CACO_EPI_BIAS_F16, st));
+    CK(attention_text(qkv, text_mask, att, B, T, c.text_heads, D / c.text_heads, st));
+    CK(lin(m, att, D, l.o_w, D, l.o_b, x, D, x, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
+    CK(layernorm(x, l.ln1_g, l.ln1_b, c.ln_eps, a, a16, Ri, D, st));
+    // cross-attention to the audio tokens (roberta.py:205-211; key mask = audio mask, :358-361)
+    CK(lin(m, a16, D, d.cq_w, D, d.cq_b, nullptr, 0, q, D, Ri, D, CACO_EPI_BIAS_F16, st));
+    CK(lin(m, ah16, D, d.ckv_w, D, d.ckv_b, nullptr, 0, kv, 2 * D, RAi, 2 * D, CACO_EPI_BIAS_F16, st));
+    CK(attention_cross(q, D, kv, audio_mask, att, B, T, S, c.text_heads, D / c.text_heads, st));
+    CK(lin(m, att, D, d.co_w, D, d.co_b, a, D, a, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
+    CK(layernorm(a, d.lnc_g, d.lnc_b, c.ln_eps, cc, c16, Ri, D, st));
+    // MLP
+    CK(lin(m, c16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, Ri, F, CACO_EPI_BIAS_GELU_F16, st));
+    CK(lin(m, mlp, F, l.fc2_w, F, l.fc2_b, cc, D, cc, D, Ri, D, CACO_EPI_BIAS_RESID_F32, st));
+    CK(layernorm(cc, l.ln2_g, l.ln2_b, c.ln_eps, x, x16, Ri, D, st));
+  }
+  // vocabulary projection into the padded buffer, then the [R, vocab] rows out (50265 is odd: no aligned row pitch exists)
+  CK(lin(m, x16, D, m->dproj_w, D, m->dproj_b, nullptr, 0, logp, Vp, Ri, Vp, CACO_EPI_BIAS_F32, st));
+  e = cudaMemcpy2DAsync(logits_out, (size_t)V * 4, logp, (size_t)Vp * 4, (size_t)V * 4, R, cudaMemcpyDeviceToDevice, st);
+  return (int)e;
+}
+
 }  // namespace caco
 
 extern "C" {
+
+int caco_model_decoder_logits(caco_model* m, const float* text_hidden, const float* text_mask, const float* audio_hidden,
+                              const float* audio_mask, int batch, int T, int S, float* logits_out, void* stream) {
+  if (!m) return CACO_ERR_ARG;
+  return caco::decoder_logits(m, text_hidden, text_mask, audio_hidden, audio_mask, batch, T, S, logits_out, (cudaStream_t)stream);
+}
+int caco_model_decoder_vocab(const caco_model* m) { return (m && m->packed) ? m->dec_vocab : 0; }
 
 const char* caco_last_error(void) { return caco::g_err; }
 
@@ -405,15 +557,14 @@ void caco_model_destroy(caco_model* m) {
   cudaDeviceSynchronize();
   if (m->arena16) cudaFree(m->arena16);
   if (m->arena32) cudaFree(m->arena32);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (m->ws[i]) cudaFree(m->ws[i]);
   delete m;
 }
 
 int caco_model_set_tensor(caco_model* m, const char* key, const float* dev_ptr, int64_t numel) {
   if (!m || !key || !dev_ptr || numel <= 0) return CACO_ERR_ARG;
-  if (strncmp(key, "decoder_module.", 15) == 0) return 1;   // captioning head: not on this path
-  m->w[key] = caco_model::T{dev_ptr, numel};
+  m->w[key] = caco_model::T{dev_ptr, numel};     // decoder_module.* included: packed when the whole head is registered
   m->packed = false;
   return 0;
 }

@@ -166,6 +166,52 @@ def compute_all_class_embeddings(model: CACO, tokenizer: Any, class_list: List[s
     return embed_text_ids(model, tb["text_input_ids"], tb["text_mask"], batch_size)
 
 
+# ------------------------------------------------------------------------------------------------------- captioning
+@torch.no_grad()
+def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id: int = 0, eos_id: int = 2,
+                       max_decode_length: int = 100, temperature: float = 0.0,
+                       generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """The loop of decode_caption (eval_caco_torch.py:411-472) on token ids, for a whole batch: BOS, then one token per step
+    from ``get_decoder_logits`` on the sequence so far (the reference re-runs the decoder on the full prefix every step too;
+    its own call passes keyword names ``RobertaDecoder.forward`` does not have — SURVEY.md 2 row 6 — so the call it means,
+    ``CACO.get_decoder_logits``, is the one made here).  temperature 0: greedy (device arg-max, ``caco_topk_rows``);
+    > 0: ``softmax(logits / temperature)`` sampled with torch.multinomial as the reference does.  Returns [batch, <= L+1] ids;
+    a sequence that has produced EOS keeps emitting EOS."""
+    _, audio_hidden = model.get_audio_embedding(audio_patches=audio_batch["audio_patches"],
+                                                audio_time_inds=audio_batch["audio_time_inds"],
+                                                audio_freq_inds=audio_batch["audio_freq_inds"],
+                                                audio_mask=audio_batch["audio_mask"], deterministic=True,
+                                                return_hidden_state=True, normalize=False)
+    dev = audio_hidden.device
+    B = audio_hidden.shape[0]
+    generated = torch.full((B, 1), bos_id, dtype=torch.long, device=dev)
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    for _ in range(max_decode_length):
+        text_mask = torch.ones(generated.shape, dtype=torch.float32, device=dev)
+        logits = model.get_decoder_logits(audio_hidden, audio_batch["audio_mask"], generated, text_mask)
+        last = logits[:, -1, :].contiguous()
+        if temperature > 0:
+            nxt = torch.multinomial(torch.softmax(last / temperature, dim=-1), num_samples=1, generator=generator)
+        else:
+            nxt = ops.topk_rows(last, 1).long()
+        nxt = torch.where(done[:, None], torch.full_like(nxt, eos_id), nxt)
+        generated = torch.cat([generated, nxt], dim=1)
+        done = done | (nxt[:, 0] == eos_id)
+        if bool(done.all()):
+            break
+    return generated
+
+
+@torch.no_grad()
+def decode_caption(model: CACO, tokenizer: Any, audio_batch: Dict[str, torch.Tensor], max_decode_length: int = 100,
+                   temperature: float = 0.1) -> str:
+    """eval_caco_torch.py:411-472 (same arguments and return value: the decoded caption of the first clip)."""
+    if model.decoder_module is None:
+        raise ValueError("Model does not have a decoder module. Load with use_decoder=True.")
+    ids = decode_caption_ids(model, audio_batch, tokenizer.bos_token_id, tokenizer.eos_token_id, max_decode_length, temperature)
+    return tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip()
+
+
 # ------------------------------------------------------------------------------------------------------- zero-shot
 @torch.no_grad()
 def zero_shot_logits(model: CACO, audio_embeddings: torch.Tensor, all_text_embeddings: torch.Tensor) -> torch.Tensor:

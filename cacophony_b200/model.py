@@ -235,9 +235,8 @@ class RobertaDecoder(nn.Module):
 # CACO
 # ------------------------------------------------------------------------------------------------------
 class CACO(nn.Module):
-    """Drop-in for src/caco_torch/caco.py:82-261 (inference path; the captioning decoder is out of scope:
-    ``decoder_module.*`` checkpoint keys are accepted and ignored, ``get_decoder_logits`` raises the
-    reference's own ValueError)."""
+    """Drop-in for src/caco_torch/caco.py:82-261 (inference path, including ``get_decoder_logits`` of the captioning head when
+    the model was built with a ``decoder_config``, as ``create_caco_model`` does)."""
 
     def __init__(self, audio_config: AudioTransformerConfig, text_config: RobertaConfig, caco_config: CACOConfig,
                  decoder_config: Optional[RobertaConfig] = None):
@@ -251,7 +250,8 @@ class CACO(nn.Module):
         self.text_module = RobertaModel(text_config)
         self.text_proj = _Linear(text_config.hidden_size, caco_config.projection_size)
         self.logit_scale = nn.Parameter(torch.tensor(caco_config.logit_scale_init_value), requires_grad=False)
-        self.decoder_module = None       # caco.py:118-121: captioning head, not on this path
+        # caco.py:118-121: the captioning head exists iff a decoder config is given (create_caco_model gives one)
+        self.decoder_module = RobertaDecoder(decoder_config) if decoder_config is not None else None
         self._handle: Optional[int] = None
         self._packed_key = None
         self._side_stream = None
@@ -260,8 +260,16 @@ class CACO(nn.Module):
 
     # ---- state handling ---------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        """Accepts the reference checkpoint layouts' tensors; ``decoder_module.*`` is ignored."""
-        sd = {k: v for k, v in state_dict.items() if not k.startswith("decoder_module.")}
+        """Accepts the reference checkpoint layouts' tensors.  ``decoder_module.*`` tensors are loaded when this
+        model has the captioning head and dropped otherwise; an encoder-only state_dict leaves the head as it is."""
+        has_dec = any(k.startswith("decoder_module.") for k in state_dict)
+        if self.decoder_module is None:
+            sd = {k: v for k, v in state_dict.items() if not k.startswith("decoder_module.")}
+        elif not has_dec:
+            sd = dict(state_dict)
+            sd.update({"decoder_module." + k: v for k, v in self.decoder_module.state_dict().items()})
+        else:
+            sd = state_dict
         out = super().load_state_dict(sd, strict=strict, assign=assign)
         self._packed_key = None
         return out
@@ -414,8 +422,35 @@ class CACO(nn.Module):
                                     return_hidden_state=False, normalize=True)
         return self.similarity(a, t)
 
-    def get_decoder_logits(self, *args, **kwargs):
-        raise ValueError("Decoder module not initialized")       # caco.py:223-224
+    @torch.no_grad()
+    def get_decoder_logits(self, audio_hidden_state: torch.Tensor, audio_mask: torch.Tensor, text_input_ids: torch.Tensor,
+                           text_mask: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
+        """caco.py:214-240: captioning logits [batch, T, vocab] — text tower hidden state -> RobertaDecoder (causal
+        self-attention, cross-attention to ``audio_hidden_state`` [batch, S, hidden], GELU MLP, vocabulary projection)."""
+        if self.decoder_module is None:
+            raise ValueError("Decoder module not initialized")       # caco.py:223-224
+        if not deterministic:
+            raise ValueError("cacophony_b200 implements the inference path only (deterministic=True)")
+        h = self._ensure_packed()
+        dev = self._device()
+        _, text_hidden = self.get_text_embedding(text_input_ids, text_mask, deterministic=True, return_hidden_state=True)
+        ah = _as(audio_hidden_state, torch.float32, dev, "audio_hidden_state")
+        am = _as(audio_mask, torch.float32, dev, "audio_mask")
+        tm = _as(text_mask, torch.float32, dev, "text_mask")
+        if ah.dim() != 3 or ah.shape[-1] != self.audio_config.hidden_size or tuple(am.shape) != tuple(ah.shape[:2]):
+            raise ValueError("audio_hidden_state: expected [batch, seq, hidden] with audio_mask [batch, seq]")
+        B, T, _ = text_hidden.shape
+        if ah.shape[0] != B:
+            raise ValueError("audio and text batch sizes differ")
+        lib = L.load()
+        V = int(lib.caco_model_decoder_vocab(h))
+        if V <= 0:
+            raise ValueError("Decoder module not initialized")
+        logits = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.caco_model_decoder_logits(h, L.ptr(text_hidden), L.ptr(tm), L.ptr(ah), L.ptr(am), B, T, int(ah.shape[1]),
+                                                  L.ptr(logits), L.stream_ptr()), "caco_model_decoder_logits")
+        return logits
 
     def forward(self, audio_patches, audio_time_inds, audio_freq_inds, audio_mask, text_input_ids, text_mask,
                 deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -194,7 +194,8 @@ void caco_model_destroy(caco_model* m);
 /* Register one f32 DEVICE tensor of the reference state_dict by its key, e.g.
  * "audio_module.layers.3.mlp.fc1.weight".  The pointer must stay valid until caco_model_pack returns
  * for GEMM weights (they are copied to f16) and for the model's lifetime for everything else
- * (biases, LayerNorm params, embeddings are used in place).  Unknown keys ("decoder_module.*") -> 1. */
+ * (biases, LayerNorm params, embeddings are used in place).  decoder_module.* tensors are optional: when the whole captioning
+ * head is registered it is packed too (caco_model_decoder_logits). */
 int caco_model_set_tensor(caco_model* m, const char* key, const float* dev_ptr, int64_t numel);
 int caco_model_pack(caco_model* m, void* stream);
 /* Per-handle execution option (names as in caco_set_default_option; a new handle starts from the library defaults).
@@ -211,6 +212,19 @@ int caco_model_audio_embedding(caco_model* m, const float* patches, const float*
 /* CACO.get_text_embedding (caco.py:152-177).  mask [batch, T] f32; position_ids may be NULL. */
 int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* mask, const int64_t* position_ids,
                               int batch, int T, int normalize, float* emb_out, float* hidden_out, void* stream);
+/* CACO.get_decoder_logits minus the text tower (caco.py:214-240, RobertaDecoder.forward roberta.py:337-373; SURVEY.md 8 row
+ * f-4): text_hidden [batch, T, hidden] f32 = the text tower's final hidden state (hidden_out of caco_model_text_embedding),
+ * audio_hidden [batch, S, hidden] f32 = the audio tower's hidden_out, masks f32 (1 = keep).  Causal self-attention, cross-attention
+ * to the audio tokens, GELU MLP per layer (post-LN), then decoder_proj.  logits_out [batch, T, vocab] f32.  Needs the
+ * decoder_module.* tensors registered before caco_model_pack (CACO_ERR_STATE otherwise).  caco_model_decoder_vocab: the
+ * vocabulary size of the packed head (0 = none). */
+int caco_model_decoder_logits(caco_model* m, const float* text_hidden, const float* text_mask, const float* audio_hidden,
+                              const float* audio_mask, int batch, int T, int S, float* logits_out, void* stream);
+int caco_model_decoder_vocab(const caco_model* m);
+/* cross-attention core used by it: q [batch*Tq, heads*64] f16 (row pitch ldq), kv [batch*Skv, 2*heads*64] f16 (k | v),
+ * key_mask [batch, Skv] f32, out [batch*Tq, heads*64] f16 (roberta.py:76-102 with key_value_states). */
+int caco_attention_cross(const void* q, int ldq, const void* kv, const float* key_mask, void* out, int batch, int Tq, int Skv,
+                         int heads, int dh, void* stream);
 /* waveform-in convenience: frontend + get_audio_embedding in one call (encode_audio). */
 int caco_model_encode_audio(caco_model* m, const float* wave, int batch, int n_samples, int max_patches, int normalize,
                             float* emb_out, void* stream);

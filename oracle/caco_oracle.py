@@ -288,6 +288,49 @@ def get_text_embedding(sd, ids, mask, normalize=False, r=None, taps=None, heads:
     return emb, hid
 
 
+# ------------------------------------------------------------------------------------------
+# captioning decoder    (src/caco_torch/text_models/roberta.py:329-373, caco.py:214-240)
+# ------------------------------------------------------------------------------------------
+def _bert_attention(sd, P, x, kv_src, bias, heads, r):
+    """RobertaAttention (roberta.py:56-147): q from x, k / v from kv_src, additive bias, dense + post-LN residual."""
+    B, Tq, D = x.shape
+    dh = D // heads
+    q = linear(x, sd[P + "self.query.weight"], sd[P + "self.query.bias"], r).reshape(B, Tq, heads, dh).transpose(1, 2)
+    k = linear(kv_src, sd[P + "self.key.weight"], sd[P + "self.key.bias"], r).reshape(B, -1, heads, dh).transpose(1, 2)
+    v = linear(kv_src, sd[P + "self.value.weight"], sd[P + "self.value.bias"], r).reshape(B, -1, heads, dh).transpose(1, 2)
+    w = torch.softmax(_ra(q, r) @ _ra(k, r).transpose(-1, -2) / math.sqrt(dh) + bias, dim=-1)
+    o = (_ra(w, r) @ _ra(v, r)).transpose(1, 2).reshape(B, Tq, D)
+    o = linear(o, sd[P + "output.dense.weight"], sd[P + "output.dense.bias"], r)
+    return layer_norm(o + x, sd[P + "output.LayerNorm.weight"], sd[P + "output.LayerNorm.bias"])
+
+
+def decoder_logits(sd, text_hidden, text_mask, audio_hidden, audio_mask, heads: int = 12, r=None):
+    """RobertaDecoder.forward (roberta.py:337-373): causal & padded self-attention (:346-355), cross-attention to the audio
+    tokens with the audio key mask (:358-361, layer :205-211), GELU MLP (:150-178), decoder_proj (:372)."""
+    B, T, _ = text_hidden.shape
+    neg = float("-inf")
+    allow = torch.tril(torch.ones(T, T, dtype=torch.bool))[None, None] & (text_mask != 0)[:, None, None, :]
+    self_bias = torch.zeros(B, 1, T, T).masked_fill(~allow, neg)
+    cross_bias = torch.zeros(B, 1, 1, audio_mask.shape[1]).masked_fill((audio_mask == 0)[:, None, None, :], neg)
+    x = text_hidden
+    i = 0
+    while f"decoder_module.encoder.layers.{i}.intermediate.dense.weight" in sd:
+        P = f"decoder_module.encoder.layers.{i}."
+        a = _bert_attention(sd, P + "attention.", x, x, self_bias, heads, r)
+        c = _bert_attention(sd, P + "crossattention.", a, audio_hidden, cross_bias, heads, r)
+        h = torch.nn.functional.gelu(linear(c, sd[P + "intermediate.dense.weight"], sd[P + "intermediate.dense.bias"], r))
+        y = linear(h, sd[P + "output.dense.weight"], sd[P + "output.dense.bias"], r)
+        x = layer_norm(y + c, sd[P + "output.LayerNorm.weight"], sd[P + "output.LayerNorm.bias"])
+        i += 1
+    return linear(x, sd["decoder_module.decoder_proj.weight"], sd["decoder_module.decoder_proj.bias"], r)
+
+
+def get_decoder_logits(sd, audio_hidden, audio_mask, ids, text_mask, r=None):
+    """CACO.get_decoder_logits (caco.py:214-240): text tower hidden state -> decoder."""
+    _, text_hidden = get_text_embedding(sd, ids, text_mask, r=r)
+    return decoder_logits(sd, text_hidden, text_mask, audio_hidden, audio_mask, r=r)
+
+
 def contrastive_logits(sd, a_emb, t_emb):
     """caco.py:208-210: scale = exp(logit_scale); (scale·A)·Tᵀ and (scale·T)·Aᵀ."""
     s = torch.exp(sd["logit_scale"])

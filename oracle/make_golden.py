@@ -40,6 +40,9 @@ MODEL_CASES = {
                           cap_lens=[8, 10, 12], T=100, max_patches=500),
     # checkpoint-like outliers (oracle/weights.py::_apply_outliers): LayerNorm gains x 30 in six channels, residual channels at
     # +-300, fc1 pre-activations near 1e3 — the case the fp16-operand scheme has to survive (or the split-weight mode)
+    # with the captioning head (4 decoder layers, roberta.py:329-373): get_decoder_logits
+    "model_s4_decoder": dict(seed=4, sharp=1.0, decoder_layers=4, clip_lens=[80000, 48000], zero_tail=[0, 0],
+                             cap_lens=[24, 9], T=24, max_patches=256),
     "model_s3_outlier": dict(seed=3, sharp=1.0, outlier=True, clip_lens=[160000, 80000, 40000], zero_tail=[0, 0, 0],
                              cap_lens=[32, 13, 6], T=32, max_patches=500),
 }
@@ -101,10 +104,11 @@ def main():
     for name, c in MODEL_CASES.items():
         if only and name not in only:
             continue
-        sd = W.make_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
+        sd = W.make_state_dict(c["seed"], c["sharp"], c.get("outlier", False), decoder_layers=c.get("decoder_layers", 0))
         ref = create_caco_model().eval()
         missing, unexpected = ref.load_state_dict(sd, strict=False)
         assert not unexpected and all(k.startswith("decoder_module") for k in missing)
+        assert not (c.get("decoder_layers") and missing)
         waves, ids, mask = case_inputs(c)
         cfg = E.DatasetConfig(patches_seq_len=c["max_patches"])
         bs = [E.prepare_audio_batch(torch.from_numpy(w)[None], cfg, "cpu") for w in waves]
@@ -120,6 +124,11 @@ def main():
         if len(waves) == len(c["cap_lens"]):
             at, ta = ref(**ab, text_input_ids=ids_t, text_mask=mask_t)
             out["at_logits"], out["ta_logits"] = at, ta
+        if c.get("decoder_layers"):
+            dl = ref.get_decoder_logits(a_hid, ab["audio_mask"], ids_t, mask_t)          # [B, T, 50265]
+            out["decoder_logits_sub"] = dl[:, :, ::97].contiguous()
+            out["decoder_logits_last_valid"] = torch.stack([dl[b, n - 1] for b, n in enumerate(c["cap_lens"])])
+            out["decoder_argmax"] = dl.argmax(-1)
         logits = torch.exp(ref.logit_scale) * a_n @ t_n.T                 # eval_caco_torch.py:330
         out["zs_logits"] = logits
         out["zs_top1"] = torch.argsort(-logits, dim=-1)[:, 0]

@@ -35,7 +35,7 @@ LOGIT_SCALE_INIT = 2.6592
 
 
 def param_spec(audio_layers: int = AUDIO_LAYERS, text_layers: int = TEXT_LAYERS,
-               vocab: int = VOCAB) -> List[Tuple[str, Tuple[int, ...], str]]:
+               vocab: int = VOCAB, decoder_layers: int = 0) -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, kind) for every tensor on the encoder path, in generation order.
 
     Key names: reference ``state_dict``; ``decoder_module.*`` is out of scope.
@@ -90,6 +90,19 @@ def param_spec(audio_layers: int = AUDIO_LAYERS, text_layers: int = TEXT_LAYERS,
           ("text_module.pooler.value_proj.weight", (D, D), "lin_w"),
           ("text_module.pooler.value_proj.bias", (D,), f"lin_b:{D}"),
           ("text_proj.weight", (D, D), "lin_w"), ("text_proj.bias", (D,), f"lin_b:{D}")]
+    # captioning head (roberta.py:329-373), APPENDED so that the encoder-path tensors of a seed do not depend on it
+    for i in range(decoder_layers):
+        p = f"decoder_module.encoder.layers.{i}."
+        for blk in ("attention", "crossattention"):
+            for nm in ("query", "key", "value"):
+                s += [(p + f"{blk}.self.{nm}.weight", (D, D), "lin_w"), (p + f"{blk}.self.{nm}.bias", (D,), f"lin_b:{D}")]
+            s += [(p + f"{blk}.output.dense.weight", (D, D), "lin_w"), (p + f"{blk}.output.dense.bias", (D,), f"lin_b:{D}"),
+                  (p + f"{blk}.output.LayerNorm.weight", (D,), "ln_w"), (p + f"{blk}.output.LayerNorm.bias", (D,), "ln_b")]
+        s += [(p + "intermediate.dense.weight", (F, D), "lin_w"), (p + "intermediate.dense.bias", (F,), f"lin_b:{D}"),
+              (p + "output.dense.weight", (D, F), "lin_w"), (p + "output.dense.bias", (D,), f"lin_b:{F}"),
+              (p + "output.LayerNorm.weight", (D,), "ln_w"), (p + "output.LayerNorm.bias", (D,), "ln_b")]
+    if decoder_layers:
+        s += [("decoder_module.decoder_proj.weight", (vocab, D), "lin_w"), ("decoder_module.decoder_proj.bias", (vocab,), f"lin_b:{D}")]
     return s
 
 

@@ -63,14 +63,22 @@ def test_mel_filterbank_matches_torchaudio_formula(lib):
 def test_state_dict_keys_match_reference_layout():
     from oracle import weights as W
     m = cb.create_caco_model()
-    want = {n: tuple(s) for n, s, _ in W.param_spec()}
+    want = {n: tuple(s) for n, s, _ in W.param_spec(decoder_layers=4)}      # the reference's 465 tensors
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    assert got == want
-    sd = {k: torch.zeros(s) for k, s in want.items()}
-    sd["decoder_module.layers.0.attention.self.query.weight"] = torch.zeros(768, 768)   # ignored (captioning head)
-    m.load_state_dict(sd)
+    assert got == want and len(got) == 465
+    if os.path.isdir("/root/reference/src/caco_torch"):                       # and literally the reference's own state_dict
+        from oracle import ref_loader
+        ref = ref_loader.load()[0]()
+        assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == got
+    enc = {k: torch.zeros(s) for k, s in want.items() if not k.startswith("decoder_module.")}
+    m.load_state_dict(enc)                        # an encoder-only checkpoint leaves the captioning head as it is
+    m.load_state_dict({k: torch.zeros(s) for k, s in want.items()})
     with pytest.raises(RuntimeError):
-        m.load_state_dict({k: v for k, v in sd.items() if k != "text_proj.bias"})
+        m.load_state_dict({k: v for k, v in enc.items() if k != "text_proj.bias"})
+    a_cfg = cb.AudioTransformerConfig(768, 12, 8, 3072, 256, 512, 8, 0.0, 0.0)
+    headless = cb.CACO(a_cfg, cb.RobertaConfig(), cb.CACOConfig())            # decoder_config=None: caco.py:118-121
+    assert headless.decoder_module is None and len(headless.state_dict()) == 465 - 106
+    headless.load_state_dict({k: torch.zeros(s) for k, s in want.items()})    # decoder tensors of a checkpoint are dropped
 
 
 def test_reference_signatures_and_defaults():
@@ -95,8 +103,12 @@ def test_no_cpu_fallback():
         m.get_text_embedding(torch.zeros(1, 4, dtype=torch.long), torch.ones(1, 4))
     with pytest.raises(RuntimeError, match="CUDA"):
         cb.prepare_audio_batch(torch.zeros(1, 16000), cb.DatasetConfig(), "cpu")
+    a_cfg = cb.AudioTransformerConfig(768, 1, 8, 3072, 256, 512, 8, 0.0, 0.0)
+    headless = cb.CACO(a_cfg, cb.RobertaConfig(vocab_size=10, num_hidden_layers=1), cb.CACOConfig())
     with pytest.raises(ValueError, match="Decoder module not initialized"):
-        m.get_decoder_logits()
+        headless.get_decoder_logits(None, None, None, None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.get_decoder_logits(torch.zeros(1, 8, 768), torch.ones(1, 8), torch.zeros(1, 4, dtype=torch.long), torch.ones(1, 4))
 
 
 def test_product_never_imports_oracle():

@@ -91,8 +91,10 @@ def test_drivers_refuse_cpu_and_missing_tokenizer():
 
 def test_load_caco_torch_accepts_the_reference_checkpoint_layouts():
     from oracle import weights as W
-    sd = {n: torch.zeros(s) for n, s, _ in W.param_spec()}
-    sd["decoder_module.layers.0.output.dense.bias"] = torch.zeros(768)            # captioning head: ignored
+    sd = {n: torch.zeros(s) for n, s, _ in W.param_spec(decoder_layers=4)}      # a full checkpoint incl. the captioning head
+    out = ev.load_caco_torch(None, "cpu", tokenizer="tok",
+                             state_dict={k: v for k, v in sd.items() if not k.startswith("decoder_module.")})    # encoder-only
+    assert out["model"].decoder_module is not None
     for wrap in (lambda d: d, lambda d: {"state_dict": d}, lambda d: {"model_state_dict": d, "epoch": 3}):
         out = ev.load_caco_torch(None, "cpu", tokenizer="tok", state_dict=wrap(sd))
         assert set(out) == {"model", "tokenizer", "device"} and out["tokenizer"] == "tok"

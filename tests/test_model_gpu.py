@@ -23,12 +23,12 @@ REL_TOL = 1e-3          # BASELINE.json north_star: embeddings and logits within
 _MODELS = {}
 
 
-def _model(seed, sharp, synthetic_state_dict, outlier=False):
-    key = (seed, sharp, outlier)
+def _model(seed, sharp, synthetic_state_dict, outlier=False, decoder_layers=0):
+    key = (seed, sharp, outlier, decoder_layers)
     if key not in _MODELS:
         _MODELS.clear()
         m = cb.create_caco_model()
-        m.load_state_dict(synthetic_state_dict(seed, sharp, outlier))
+        m.load_state_dict(synthetic_state_dict(seed, sharp, outlier, decoder_layers))
         _MODELS[key] = m.to("cuda")
     return _MODELS[key]
 
@@ -43,7 +43,7 @@ def _audio_batch(waves, max_patches):
 def test_model_matches_reference_golden(name, golden_dir, synthetic_state_dict):
     c = MODEL_CASES[name]
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    model = _model(c["seed"], c["sharp"], synthetic_state_dict, c.get("outlier", False))
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict, c.get("outlier", False), c.get("decoder_layers", 0))
     waves, ids, mask = case_inputs(c)
     ab = _audio_batch(waves, c["max_patches"])
     ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
@@ -196,6 +196,52 @@ def test_copies_of_a_model_own_their_handles(synthetic_state_dict):
     assert torch.equal(model.encode_text(ids, mask), t0)
 
 
+def test_decoder_logits_and_greedy_decode(golden_dir, synthetic_state_dict):
+    """Row f-4: CACO.get_decoder_logits (caco.py:214-240) against the logits the reference produced (golden) and the CPU
+    oracle — tolerance: 1e-3 of the logits' spread per row, the bar of the rest of the path — and the batched greedy
+    decode loop (eval_caco_torch.py:411-472's loop) against the same loop run on the oracle."""
+    from cacophony_b200 import eval as ev
+    name = "model_s4_decoder"
+    c = MODEL_CASES[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict, False, c["decoder_layers"])
+    waves, ids, mask = case_inputs(c)
+    ab = _audio_batch(waves, c["max_patches"])
+    ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    _, a_hid = model.get_audio_embedding(**ab)
+    dl = model.get_decoder_logits(a_hid, ab["audio_mask"], ids_t, mask_t)
+    assert dl.shape == (2, c["T"], 50265) and torch.isfinite(dl).all()
+    valid = mask.astype(bool)
+    sub = dl[:, :, ::97].cpu().numpy()
+    ref = g["decoder_logits_sub"]
+    err = np.linalg.norm(sub[valid] - ref[valid], axis=-1) / np.linalg.norm(ref[valid] - ref[valid].mean(-1, keepdims=True), axis=-1)
+    print(name, "decoder logits: row error / row spread", float(err.max()))
+    assert err.max() < 2e-3
+    last = torch.stack([dl[b, n - 1] for b, n in enumerate(c["cap_lens"])]).cpu().numpy()
+    np.testing.assert_allclose(last, g["decoder_logits_last_valid"], atol=3e-3)
+    # arg-max agrees with the reference wherever its own top-2 margin is clear
+    top2 = np.sort(g["decoder_logits_last_valid"], -1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-2
+    assert np.array_equal(last.argmax(-1)[clear], g["decoder_logits_last_valid"].argmax(-1)[clear])
+    with pytest.raises(ValueError):
+        model.get_decoder_logits(a_hid[:, :, :100], ab["audio_mask"], ids_t, mask_t)
+    # greedy decode, 6 steps, against the oracle's loop
+    sd = synthetic_state_dict(c["seed"], c["sharp"], False, c["decoder_layers"])
+    out = ev.decode_caption_ids(model, ab, bos_id=0, eos_id=2, max_decode_length=6, temperature=0.0)
+    assert out.shape[0] == 2 and out.shape[1] <= 7 and int(out[0, 0]) == 0
+    rb = O.prepare_audio_batch(waves, c["max_patches"])
+    _, r_hid = O.get_audio_embedding(sd, rb["audio_patches"], rb["audio_time_inds"], rb["audio_freq_inds"], rb["audio_mask"])
+    gen = torch.zeros((2, 1), dtype=torch.long)
+    for step in range(out.shape[1] - 1):
+        lg = O.get_decoder_logits(sd, r_hid, rb["audio_mask"], gen, torch.ones(gen.shape))[:, -1]
+        srt = lg.sort(-1).values
+        nxt = out[:, step + 1].cpu()
+        for b in range(2):                        # identical token wherever the oracle's margin is clear; else follow ours
+            if float(srt[b, -1] - srt[b, -2]) > 1e-2 and int(gen[b].eq(2).any()) == 0:
+                assert int(lg[b].argmax()) == int(nxt[b]), (step, b)
+        gen = torch.cat([gen, nxt[:, None]], dim=1)
+
+
 def test_encode_audio_alias_equals_two_step(synthetic_state_dict):
     c = MODEL_CASES["model_s0"]
     model = _model(c["seed"], c["sharp"], synthetic_state_dict)
@@ -223,8 +269,10 @@ def test_batch_invariance_and_padding_rows(synthetic_state_dict):
 def test_errors_mirror_reference_behaviour(synthetic_state_dict):
     c = MODEL_CASES["model_s0"]
     model = _model(c["seed"], c["sharp"], synthetic_state_dict)
+    a_cfg = cb.AudioTransformerConfig(768, 1, 8, 3072, 256, 512, 8, 0.0, 0.0)
+    no_head = cb.CACO(a_cfg, cb.RobertaConfig(vocab_size=100, num_hidden_layers=1), cb.CACOConfig())     # decoder_config=None
     with pytest.raises(ValueError, match="Decoder module not initialized"):
-        model.get_decoder_logits(None, None, None, None)
+        no_head.get_decoder_logits(None, None, None, None)
     with pytest.raises(ValueError):
         model.get_audio_embedding(torch.zeros(1, 10, 255).cuda(), torch.zeros(1, 10).cuda(), torch.zeros(1, 10).cuda(),
                                   torch.ones(1, 10).cuda())

@@ -68,7 +68,7 @@ def _rel_rows(x, y):
 def test_model_matches_reference(name, golden_dir, synthetic_state_dict):
     c = MODEL_CASES[name]
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
+    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False), c.get("decoder_layers", 0))
     waves, ids, mask = case_inputs(c)
     ab = O.prepare_audio_batch(waves, c["max_patches"])
     ids, mask = torch.from_numpy(ids), torch.from_numpy(mask)
@@ -99,7 +99,7 @@ def test_rounding_emulation_is_within_design_budget(golden_dir, synthetic_state_
     precision scheme itself (not a kernel) is wrong."""
     c = MODEL_CASES["model_s0"]
     g = np.load(os.path.join(golden_dir, "model_s0.npz"))
-    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False))
+    sd = synthetic_state_dict(c["seed"], c["sharp"], c.get("outlier", False), c.get("decoder_layers", 0))
     waves, ids, mask = case_inputs(c)
     ab = O.prepare_audio_batch(waves[:2], c["max_patches"])
     r = O.Rounding.fp16()
@@ -108,3 +108,20 @@ def test_rounding_emulation_is_within_design_budget(golden_dir, synthetic_state_
     t, _ = O.get_text_embedding(sd, torch.from_numpy(ids[:2]), torch.from_numpy(mask[:2]), normalize=True, r=r)
     assert _rel_rows(a, g["audio_emb"][:2]) < 1e-3
     assert _rel_rows(t, g["text_emb"][:2]) < 1e-3
+
+
+def test_decoder_logits_match_reference(golden_dir, synthetic_state_dict):
+    """Row f-4: the oracle's restatement of CACO.get_decoder_logits (caco.py:214-240, roberta.py:329-373) against the golden
+    logits the reference produced on the same synthetic captioning head."""
+    c = MODEL_CASES["model_s4_decoder"]
+    g = np.load(os.path.join(golden_dir, "model_s4_decoder.npz"))
+    sd = synthetic_state_dict(c["seed"], c["sharp"], False, c["decoder_layers"])
+    waves, ids, mask = case_inputs(c)
+    ab = O.prepare_audio_batch(waves, c["max_patches"])
+    _, hid = O.get_audio_embedding(sd, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"])
+    dl = O.get_decoder_logits(sd, hid, ab["audio_mask"], torch.from_numpy(ids), torch.from_numpy(mask))
+    assert dl.shape == (2, 24, 50265)
+    valid = mask.astype(bool)
+    sub = dl[:, :, ::97].numpy()
+    assert np.abs(sub[valid] - g["decoder_logits_sub"][valid]).max() < 2e-4
+    assert np.array_equal(dl.argmax(-1).numpy()[valid], g["decoder_argmax"][valid])
