@@ -479,9 +479,20 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, 
     // machine better than CTA pairs (measured at M = 8192: QKV 28.0 vs 34.8 us, out 20.1 vs 25.4, fc1 50.4 vs 64.7, fc2 44.4 vs
     // 55.4 us).  Otherwise CTA-pair 256x256 tiles; activation epilogues get 16 epilogue warps.
     const long long pair_tiles = (((long long)M + 255) / 256) * (((long long)N + 255) / 256);
-    variant = opts().gemm_variant ? opts().gemm_variant
-              : (pair_tiles < 8 * (num_sms() / 2)) ? CACO_GEMM_CG1_N256
-              : ((epi == CACO_EPI_BIAS_SILU_F16 || epi == CACO_EPI_BIAS_GELU_F16) ? CACO_GEMM_CG2_N256_E16 : CACO_GEMM_CG2_N256);
+    if (opts().gemm_variant) {
+      variant = opts().gemm_variant;
+    } else if (pair_tiles < 8 * (num_sms() / 2)) {
+      // small problems are wave-quantised: compare the waves of 128x256 and 128x128 one-CTA tiles (a 128-wide tile costs
+      // ~0.55 of a 256-wide one).  M = 8192, N = 768 (text out-proj / fc2): 192 tiles = 2 waves vs 384 = 3 half-waves -> N128
+      // (measured: text tower alone 3.1 -> 2.5 ms).
+      const long long sms = num_sms();
+      const long long t256 = (((long long)M + 127) / 128) * (((long long)N + 255) / 256);
+      const long long t128 = (((long long)M + 127) / 128) * (((long long)N + 127) / 128);
+      const double c256 = (double)((t256 + sms - 1) / sms), c128 = 0.55 * (double)((t128 + sms - 1) / sms);
+      variant = (c128 < c256) ? CACO_GEMM_CG1_N128 : CACO_GEMM_CG1_N256;
+    } else {
+      variant = (epi == CACO_EPI_BIAS_SILU_F16 || epi == CACO_EPI_BIAS_GELU_F16) ? CACO_GEMM_CG2_N256_E16 : CACO_GEMM_CG2_N256;
+    }
   }
   const int cg = (variant == CACO_GEMM_CG2_N256 || variant == CACO_GEMM_CG2_N256_E16) ? 2 : 1;
   const int bn = (variant == CACO_GEMM_CG1_N128) ? 128 : 256;

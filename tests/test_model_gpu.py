@@ -396,3 +396,24 @@ def test_second_device_in_the_same_process(synthetic_state_dict):
     torch.cuda.synchronize(1)
     assert torch.equal(a0.cpu(), a1.cpu()) and torch.equal(t0.cpu(), t1.cpu())
     assert at1.device.index == 1 and torch.isfinite(at1).all()
+    # a model that has RUN on one GPU and is then moved must not keep using the old GPU's workspaces
+    import copy
+    mover = copy.deepcopy(m0)                                  # own handle, on cuda:0
+    am0 = mover.encode_audio(w.cuda(0), max_patches=500)       # workspaces now exist on cuda:0
+    gen = mover.generation()
+    mover = mover.to("cuda:1")
+    am1 = mover.encode_audio(w.cuda(1), max_patches=500)
+    torch.cuda.synchronize(1)
+    assert am1.device.index == 1 and torch.equal(am0.cpu(), am1.cpu()) and mover.generation() > gen
+    # operator-level calls follow their tensors' device, whatever the process's current device is
+    from cacophony_b200 import ops
+    assert torch.cuda.current_device() == 0
+    x1 = torch.randn(64, 768, device="cuda:1")
+    g1 = torch.ones(768, device="cuda:1")
+    y1, _ = ops.layernorm(x1, g1, torch.zeros_like(g1))
+    ref = torch.nn.functional.layer_norm(x1, (768,))
+    assert y1.device.index == 1 and float((y1 - ref).abs().max()) < 1e-4
+    top = ops.topk_rows(torch.randn(5, 40, device="cuda:1"), 3)
+    assert top.device.index == 1
+    with pytest.raises(ValueError, match="different devices"):
+        ops.layernorm(x1, g1.cuda(0), torch.zeros_like(g1))
