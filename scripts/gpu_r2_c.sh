@@ -9,3 +9,6 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpu
 kill $SMI
 timeout 600 python bench.py --workload zeroshot --steps 10 --warmup 3 > gpurun_out/bench_zeroshot.json 2> gpurun_out/bench_zeroshot.err; echo "zeroshot rc=$?"; cat gpurun_out/bench_zeroshot.json; tail -3 gpurun_out/bench_zeroshot.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm rc=$?"; cut -c1-400 gpurun_out/bench_reference.json; tail -2 gpurun_out/bench_reference.err
+timeout 300 python scripts/bench_decode.py > gpurun_out/bench_decode.jsonl 2>&1; cat gpurun_out/bench_decode.jsonl
+timeout 300 python scripts/bench_attn.py 2>&1 | tail -1
+timeout 300 python scripts/bench_frontend.py 2>&1 | tail -1
