@@ -1,4 +1,4 @@
-"""Timeline of CTA 0 of the persistent ping-pong attention kernel (clock64 stamps, see TC3_STAMP in attention_tc3.cu)."""
+"""Timeline of CTA 0 of the persistent ping-pong attention kernel (clock64 stamps, see PP_STAMP in attention_pp.cu)."""
 import ctypes as C
 import sys
 
