@@ -66,6 +66,9 @@ SIGNATURES = {
     "caco_model_text_embedding": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_model_decoder_logits": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "caco_model_decoder_vocab": (_I, [_P]),
+    "caco_model_decode_cache_bytes": (C.c_size_t, [_P, _I, _I, _I]),
+    "caco_model_decode_begin": (_I, [_P, _P, C.c_size_t, _P, _P, _I, _I, _I, _P]),
+    "caco_model_decode_step": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "caco_attention_cross": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "caco_model_encode_audio": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "caco_model_encode_audio_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

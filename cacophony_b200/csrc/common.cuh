@@ -74,6 +74,9 @@ int frontend(const float* wave, const int* lengths, int batch, int n_samples, in
              void* patches_f16, float* time_inds, float* freq_inds, float* mask, float* log_mel, cudaStream_t stream);
 int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 int cast_f32_f16_split(const float* src, void* dst, int64_t rows, int64_t K, cudaStream_t stream);
+int kv_append(const void* qkv, void* cache, const int64_t* pos, float* key_mask, int batch, int D, int capacity,
+              cudaStream_t stream);
+int topk_rows(const float* x, int rows, int cols, int ldx, int k, int* idx_out, float* val_out, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int rows,
               int dim, cudaStream_t stream);
 int audio_add_pos(float* x, const float* time_inds, const float* freq_inds, const float* freq_emb, int n_freq, int rows,

@@ -524,9 +524,149 @@ static int decoder_logits(caco_model* m, const float* text_hidden, const float* 
   return (int)e;
 }
 
+// ---------------------------------------------------------------------------------------- KV-cached captioning decode
+// The reference's decode loop (eval_caco_torch.py:411-472) re-runs text tower + decoder on the whole prefix for every new
+// token.  Both are causal, so the keys / values of earlier tokens never change: a step only has to push ONE token per sequence
+// through the 12 text layers and the 4 decoder layers, attending to cached keys / values ("KV-cached
+// sampling"; the JAX twin caches too, caco/caco.py:154-230).  The cache is caller-owned memory laid out by DecodeCache:
+//   text layers       Lt x [batch, capacity, 2D] f16   k | v of every token pushed so far
+//   decoder self      Ld x [batch, capacity, 2D] f16
+//   decoder cross     Ld x [batch * S, 2D] f16         k | v of the audio tokens, computed once by decode_begin
+//   key mask          [batch, capacity] f32            1 for the slots filled so far (what a causal mask reduces to for the
+//                                                      newest query), audio mask [batch, S] f32 (copied: the caller's may go away)
+// Same kernels and the same per-row arithmetic as the full-prefix path: masked slots contribute exp2(-inf) = 0 exactly.
+struct DecodeCache {
+  size_t self_bytes, cross_bytes, o_text, o_dself, o_cross, o_kmask, o_amask, total;
+  DecodeCache(const caco_model* m, int B, int S, int cap) {
+    const size_t D = m->cfg.hidden;
+    self_bytes = al256((size_t)B * cap * 2 * D * sizeof(__half));
+    cross_bytes = al256((size_t)B * S * 2 * D * sizeof(__half));
+    size_t off = 0;
+    o_text = off;  off += self_bytes * (size_t)m->cfg.text_layers;
+    o_dself = off; off += self_bytes * m->dl.size();
+    o_cross = off; off += cross_bytes * m->dl.size();
+    o_kmask = off; off += al256((size_t)B * cap * sizeof(float));
+    o_amask = off; off += al256((size_t)B * S * sizeof(float));
+    total = off;
+  }
+};
+
+static int decode_args_ok(caco_model* m, const void* cache, int B, int S, int cap) {
+  if (m->dl.empty() || !m->dproj_w) { set_err("decoder_module tensors were not registered%s", ""); return CACO_ERR_STATE; }
+  if (!cache || B <= 0 || S <= 0 || cap <= 0 || cap > m->cfg.max_pos || (size_t)B * S > (1u << 22) || B > (1 << 16))
+    return CACO_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(cache) & 255) return CACO_ERR_ALIGN;
+  return 0;
+}
+
+static int decode_begin(caco_model* m, void* cache, size_t cache_bytes, const float* audio_hidden, const float* audio_mask,
+                        int B, int S, int cap, cudaStream_t st) {
+  CK(ready(m, st));
+  OptionsScope scope(&m->opt);
+  CK(decode_args_ok(m, cache, B, S, cap));
+  if (!audio_hidden || !audio_mask) return CACO_ERR_ARG;
+  const DecodeCache L(m, B, S, cap);
+  if (cache_bytes < L.total) return CACO_ERR_ARG;
+  const int D = m->cfg.hidden;
+  const size_t RA = (size_t)B * S;
+  CK(ensure_ws(m, 2, al256(RA * D * sizeof(__half))));
+  __half* ah16 = (__half*)m->ws[2];
+  uint8_t* c = (uint8_t*)cache;
+  // empty self caches (masked slots are multiplied by an exact 0, so they must hold finite numbers) and an all-closed key mask
+  cudaError_t e = cudaMemsetAsync(c + L.o_text, 0, L.o_cross - L.o_text, st);
+  if (!e) e = cudaMemsetAsync(c + L.o_kmask, 0, (size_t)B * cap * sizeof(float), st);
+  if (!e) e = cudaMemcpyAsync(c + L.o_amask, audio_mask, RA * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (e) return (int)e;
+  CK(cast_f32_f16(audio_hidden, ah16, (int64_t)RA * D, st));
+  for (size_t i = 0; i < m->dl.size(); ++i)      // roberta.py:76-83 with key_value_states = the audio hidden state
+    CK(lin(m, ah16, D, m->dl[i].ckv_w, D, m->dl[i].ckv_b, nullptr, 0, c + L.o_cross + i * L.cross_bytes, 2 * D, (int)RA, 2 * D,
+           CACO_EPI_BIAS_F16, st));
+  return 0;
+}
+
+// One token per sequence: ids [B] (the newest token), pos [B] (its position = number of tokens already cached).  Writes the
+// next-token logits [B, vocab] (logits_out, may be NULL) and / or their arg-max (next_out int32 [B], may be NULL).
+static int decode_step(caco_model* m, void* cache, const int64_t* ids, const int64_t* pos, int B, int S, int cap,
+                       float* logits_out, int* next_out, cudaStream_t st) {
+  CK(ready(m, st));
+  OptionsScope scope(&m->opt);
+  CK(decode_args_ok(m, cache, B, S, cap));
+  if (!ids || !pos || (!logits_out && !next_out)) return CACO_ERR_ARG;
+  const caco_config& cf = m->cfg;
+  const DecodeCache L(m, B, S, cap);
+  const int D = cf.hidden, F = cf.ffn, V = m->dec_vocab, Vp = m->dec_vocab_pad, H = cf.text_heads, dh = D / cf.text_heads;
+  const size_t R = (size_t)B;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  const size_t o_x = carve(R * D * 4), o_x16 = carve(R * D * 2), o_a = carve(R * D * 4), o_a16 = carve(R * D * 2);
+  const size_t o_c = carve(R * D * 4), o_c16 = carve(R * D * 2), o_qkv = carve(R * 3 * D * 2), o_att = carve(R * D * 2);
+  const size_t o_q = carve(R * D * 2), o_mlp = carve(R * (size_t)F * 2), o_log = carve(R * (size_t)Vp * 4);
+  CK(ensure_ws(m, 2, off));
+  uint8_t* w = (uint8_t*)m->ws[2];
+  float *x = (float*)(w + o_x), *a = (float*)(w + o_a), *cc = (float*)(w + o_c), *logp = (float*)(w + o_log);
+  __half *x16 = (__half*)(w + o_x16), *a16 = (__half*)(w + o_a16), *c16 = (__half*)(w + o_c16), *qkv = (__half*)(w + o_qkv);
+  __half *att = (__half*)(w + o_att), *q = (__half*)(w + o_q), *mlp = (__half*)(w + o_mlp);
+  uint8_t* c = (uint8_t*)cache;
+  float* kmask = (float*)(c + L.o_kmask);
+  const float* amask = (const float*)(c + L.o_amask);
+
+  // text tower on the new token (roberta.py:35-53, 191-215): position ids are the cache positions
+  CK(text_embed_ln(ids, pos, m->word, m->pos, m->type0, m->te_g, m->te_b, cf.ln_eps, x, x16, B, 1, D, cf.vocab, cf.max_pos, st));
+  // causal self-attention block against a cache: the new token's k | v go into slot pos[b], its query sees slots 0..pos[b]
+  auto self_block = [&](const caco_model::TLayer& l, void* kv, bool open_slot) -> int {
+    CK(lin(m, x16, D, l.qkv_w, D, l.qkv_b, nullptr, 0, qkv, 3 * D, B, 3 * D, CACO_EPI_BIAS_F16, st));
+    CK(kv_append(qkv, kv, pos, open_slot ? kmask : nullptr, B, D, cap, st));
+    CK(attention_cross(qkv, 3 * D, kv, kmask, att, B, 1, cap, H, dh, st));
+    CK(lin(m, att, D, l.o_w, D, l.o_b, x, D, x, D, B, D, CACO_EPI_BIAS_RESID_F32, st));
+    return layernorm(x, l.ln1_g, l.ln1_b, cf.ln_eps, a, a16, B, D, st);
+  };
+  // GELU MLP + LayerNorm of `in` (f32 + f16 copy) back into x / x16
+  auto mlp_block = [&](const caco_model::TLayer& l, float* in, const __half* in16) -> int {
+    CK(lin(m, in16, D, l.fc1_w, D, l.fc1_b, nullptr, 0, mlp, F, B, F, CACO_EPI_BIAS_GELU_F16, st));
+    CK(lin(m, mlp, F, l.fc2_w, F, l.fc2_b, in, D, in, D, B, D, CACO_EPI_BIAS_RESID_F32, st));
+    return layernorm(in, l.ln2_g, l.ln2_b, cf.ln_eps, x, x16, B, D, st);
+  };
+  for (int i = 0; i < cf.text_layers; ++i) {
+    CK(self_block(m->tl[i], c + L.o_text + (size_t)i * L.self_bytes, i == 0));
+    CK(mlp_block(m->tl[i], a, a16));
+  }
+  // captioning decoder on the text tower's hidden state (roberta.py:337-373)
+  for (size_t i = 0; i < m->dl.size(); ++i) {
+    const caco_model::DLayer& d = m->dl[i];
+    CK(self_block(d.self_ffn, c + L.o_dself + i * L.self_bytes, false));
+    CK(lin(m, a16, D, d.cq_w, D, d.cq_b, nullptr, 0, q, D, B, D, CACO_EPI_BIAS_F16, st));
+    CK(attention_cross(q, D, c + L.o_cross + i * L.cross_bytes, amask, att, B, 1, S, H, dh, st));
+    CK(lin(m, att, D, d.co_w, D, d.co_b, a, D, a, D, B, D, CACO_EPI_BIAS_RESID_F32, st));
+    CK(layernorm(a, d.lnc_g, d.lnc_b, cf.ln_eps, cc, c16, B, D, st));
+    CK(mlp_block(d.self_ffn, cc, c16));
+  }
+  CK(lin(m, x16, D, m->dproj_w, D, m->dproj_b, nullptr, 0, logp, Vp, B, Vp, CACO_EPI_BIAS_F32, st));
+  if (next_out) CK(topk_rows(logp, B, V, Vp, 1, next_out, nullptr, st));
+  if (logits_out) {
+    cudaError_t e = cudaMemcpy2DAsync(logits_out, (size_t)V * 4, logp, (size_t)Vp * 4, (size_t)V * 4, R, cudaMemcpyDeviceToDevice, st);
+    if (e) return (int)e;
+  }
+  return 0;
+}
+
 }  // namespace caco
 
 extern "C" {
+
+size_t caco_model_decode_cache_bytes(const caco_model* m, int batch, int S, int capacity) {
+  if (!m || !m->packed || m->dl.empty() || batch <= 0 || S <= 0 || capacity <= 0) return 0;
+  return caco::DecodeCache(m, batch, S, capacity).total;
+}
+int caco_model_decode_begin(caco_model* m, void* cache, size_t cache_bytes, const float* audio_hidden, const float* audio_mask,
+                            int batch, int S, int capacity, void* stream) {
+  if (!m) return CACO_ERR_ARG;
+  return caco::decode_begin(m, cache, cache_bytes, audio_hidden, audio_mask, batch, S, capacity, (cudaStream_t)stream);
+}
+int caco_model_decode_step(caco_model* m, void* cache, const int64_t* ids, const int64_t* positions, int batch, int S,
+                           int capacity, float* logits_out, int* next_out, void* stream) {
+  if (!m) return CACO_ERR_ARG;
+  return caco::decode_step(m, cache, ids, positions, batch, S, capacity, logits_out, next_out, (cudaStream_t)stream);
+}
 
 int caco_model_decoder_logits(caco_model* m, const float* text_hidden, const float* text_mask, const float* audio_hidden,
                               const float* audio_mask, int batch, int T, int S, float* logits_out, void* stream) {

@@ -41,6 +41,30 @@ int cast_f32_f16(const float* src, void* dst, int64_t n, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// KV-cached captioning decode (engine.cu: decode_step): row b of the step's packed q | k | v GEMM output [batch, 3D] hands its
+// k | v half to slot pos[b] of that sequence's cache [batch, capacity, 2D]; the first layer of a step also opens the slot in the
+// key mask [batch, capacity] the step's attention launches read.  Positions live on the device so that a step can be replayed
+// from a CUDA graph.
+__global__ void __launch_bounds__(128)
+kv_append_kernel(const __half* __restrict__ qkv, __half* __restrict__ cache, const int64_t* __restrict__ pos,
+                 float* __restrict__ key_mask, int D, int capacity) {
+  const int b = blockIdx.x;
+  const int64_t p = pos[b];
+  if (p < 0 || p >= capacity) return;
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)b * 3 * D + D);
+  uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)b * capacity + (size_t)p) * 2 * D);
+  for (int i = threadIdx.x; i < 2 * D / 8; i += blockDim.x) dst[i] = src[i];
+  if (key_mask && threadIdx.x == 0) key_mask[(size_t)b * capacity + p] = 1.0f;
+}
+int kv_append(const void* qkv, void* cache, const int64_t* pos, float* key_mask, int batch, int D, int capacity,
+              cudaStream_t stream) {
+  if (!qkv || !cache || !pos || batch <= 0 || D <= 0 || (D & 7) || capacity <= 0) return CACO_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(cache) & 15)) return CACO_ERR_ALIGN;
+  kv_append_kernel<<<batch, 128, 0, stream>>>((const __half*)qkv, (__half*)cache, pos, key_mask, D, capacity);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 // split-weight packing: dst[r, 0:K] = fp16(w), dst[r, K:2K] = fp16(w - fp16(w))   (K % 4 == 0)
 __global__ void cast_f32_f16_split_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t rows, int64_t K) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;

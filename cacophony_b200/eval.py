@@ -167,16 +167,27 @@ def compute_all_class_embeddings(model: CACO, tokenizer: Any, class_list: List[s
 
 
 # ------------------------------------------------------------------------------------------------------- captioning
+# decode_caption_ids' default: incremental decode against a key / value cache (True) or the reference's literal loop, which
+# re-runs text tower + decoder on the whole prefix for every token (False).  Same tokens either way (tests/test_model_gpu.py).
+USE_KV_CACHE = False
+
+
 @torch.no_grad()
 def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id: int = 0, eos_id: int = 2,
                        max_decode_length: int = 100, temperature: float = 0.0,
-                       generator: Optional[torch.Generator] = None) -> torch.Tensor:
+                       generator: Optional[torch.Generator] = None, use_cache: Optional[bool] = None,
+                       use_graph: bool = False) -> torch.Tensor:
     """The loop of decode_caption (eval_caco_torch.py:411-472) on token ids, for a whole batch: BOS, then one token per step
-    from ``get_decoder_logits`` on the sequence so far (the reference re-runs the decoder on the full prefix every step too;
-    its own call passes keyword names ``RobertaDecoder.forward`` does not have — SURVEY.md 2 row 6 — so the call it means,
-    ``CACO.get_decoder_logits``, is the one made here).  temperature 0: greedy (device arg-max, ``caco_topk_rows``);
-    > 0: ``softmax(logits / temperature)`` sampled with torch.multinomial as the reference does.  Returns [batch, <= L+1] ids;
-    a sequence that has produced EOS keeps emitting EOS."""
+    from the decoder logits of the sequence so far (the reference's own call passes keyword names ``RobertaDecoder.forward``
+    does not have — SURVEY.md 2 row 6 — so the call it means, ``CACO.get_decoder_logits``, is the one made here).
+    temperature 0: greedy (device arg-max, ``caco_topk_rows``); > 0: ``softmax(logits / temperature)`` sampled with
+    torch.multinomial as the reference does.  Returns [batch, <= L+1] ids; a sequence that has produced EOS keeps emitting EOS.
+
+    use_cache (default ``USE_KV_CACHE``): False re-runs ``get_decoder_logits`` on the full prefix every step, as the reference
+    does; True pushes only the newest token through text tower and decoder against cached keys / values
+    (``CACO.decode_begin`` / ``decode_step``) — both towers are causal, so the logits are the same.
+    use_graph (with the cache): replay each step from one CUDA graph (``serving.GraphedDecodeStep``) — a step is ~140 small
+    launches, launch-bound at small batches."""
     _, audio_hidden = model.get_audio_embedding(audio_patches=audio_batch["audio_patches"],
                                                 audio_time_inds=audio_batch["audio_time_inds"],
                                                 audio_freq_inds=audio_batch["audio_freq_inds"],
@@ -186,12 +197,36 @@ def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id
     B = audio_hidden.shape[0]
     generated = torch.full((B, 1), bos_id, dtype=torch.long, device=dev)
     done = torch.zeros(B, dtype=torch.bool, device=dev)
-    for _ in range(max_decode_length):
-        text_mask = torch.ones(generated.shape, dtype=torch.float32, device=dev)
-        logits = model.get_decoder_logits(audio_hidden, audio_batch["audio_mask"], generated, text_mask)
-        last = logits[:, -1, :].contiguous()
+    if use_cache is None:
+        use_cache = USE_KV_CACHE
+    stepper = None
+    if use_cache:
+        capacity = max(1, min(int(max_decode_length), model.text_config.max_position_embeddings))
+        if use_graph:
+            from .serving import GraphedDecodeStep
+            stepper = GraphedDecodeStep(model, B, int(audio_hidden.shape[1]), capacity)
+            stepper.begin(audio_hidden, audio_batch["audio_mask"])
+        else:
+            cache = model.decode_begin(audio_hidden, audio_batch["audio_mask"], capacity)
+        pos = torch.zeros(B, dtype=torch.long, device=dev)
+    for step in range(max_decode_length):
+        if use_cache:
+            tok = generated[:, -1].contiguous()
+            if stepper is not None:
+                last, greedy = stepper.step(tok, pos)
+            elif temperature > 0:
+                last, greedy = model.decode_step(cache, tok, pos), None
+            else:
+                last, greedy = None, model.decode_step(cache, tok, pos, want_logits=False, want_next=True)
+            pos = pos + 1
+        else:
+            text_mask = torch.ones(generated.shape, dtype=torch.float32, device=dev)
+            logits = model.get_decoder_logits(audio_hidden, audio_batch["audio_mask"], generated, text_mask)
+            last, greedy = logits[:, -1, :].contiguous(), None
         if temperature > 0:
             nxt = torch.multinomial(torch.softmax(last / temperature, dim=-1), num_samples=1, generator=generator)
+        elif greedy is not None:
+            nxt = greedy.long()[:, None]
         else:
             nxt = ops.topk_rows(last, 1).long()
         nxt = torch.where(done[:, None], torch.full_like(nxt, eos_id), nxt)

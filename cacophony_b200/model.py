@@ -452,6 +452,69 @@ class CACO(nn.Module):
                                                   L.ptr(logits), L.stream_ptr()), "caco_model_decoder_logits")
         return logits
 
+    # ---- KV-cached captioning decode -------------------------------------------
+    @torch.no_grad()
+    def decode_begin(self, audio_hidden_state: torch.Tensor, audio_mask: torch.Tensor, capacity: int,
+                     cache: Optional["DecodeCache"] = None) -> "DecodeCache":
+        """Start an incremental decode for a batch of clips: allocates the key / value cache for sequences of up to ``capacity``
+        tokens and stores the cross-attention keys / values of ``audio_hidden_state`` [batch, S, hidden].  Text tower and
+        decoder are causal (roberta.py:297-310, 346-355), so ``decode_step`` on token t against the cache gives the logits
+        ``get_decoder_logits(...)[:, t]`` of the full-prefix call the reference makes every step (eval_caco_torch.py:411-472).
+        ``cache``: an earlier cache of the same (batch, S, capacity) to reset and reuse instead of allocating a new one."""
+        if self.decoder_module is None:
+            raise ValueError("Decoder module not initialized")       # caco.py:223-224
+        h = self._ensure_packed()
+        dev = self._device()
+        ah = _as(audio_hidden_state, torch.float32, dev, "audio_hidden_state")
+        am = _as(audio_mask, torch.float32, dev, "audio_mask")
+        if ah.dim() != 3 or ah.shape[-1] != self.audio_config.hidden_size or tuple(am.shape) != tuple(ah.shape[:2]):
+            raise ValueError("audio_hidden_state: expected [batch, seq, hidden] with audio_mask [batch, seq]")
+        B, S = int(ah.shape[0]), int(ah.shape[1])
+        capacity = int(capacity)
+        if not 1 <= capacity <= self.text_config.max_position_embeddings:
+            raise ValueError(f"capacity must be in [1, {self.text_config.max_position_embeddings}]")
+        lib = L.load()
+        nbytes = int(lib.caco_model_decode_cache_bytes(h, B, S, capacity))
+        if nbytes <= 0:
+            raise ValueError("Decoder module not initialized")
+        if cache is not None:
+            if (cache.batch, cache.seq, cache.capacity) != (B, S, capacity) or cache.view.numel() != nbytes or cache.view.device != dev:
+                raise ValueError("decode_begin: the cache to reuse was made for another shape or device")
+        else:
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            shift = (-buf.data_ptr()) % 256
+            cache = DecodeCache(buf, buf[shift:shift + nbytes], B, S, capacity, int(lib.caco_model_decoder_vocab(h)))
+        with torch.cuda.device(dev):
+            L.check(lib.caco_model_decode_begin(h, L.ptr(cache.view), nbytes, L.ptr(ah), L.ptr(am), B, S, capacity,
+                                                L.stream_ptr()), "caco_model_decode_begin")
+        return cache
+
+    @torch.no_grad()
+    def decode_step(self, cache: "DecodeCache", token_ids: torch.Tensor, positions: torch.Tensor,
+                    logits_out: Optional[torch.Tensor] = None, next_out: Optional[torch.Tensor] = None,
+                    want_logits: bool = True, want_next: bool = False):
+        """Push one token per sequence (``token_ids`` [batch] int64 at ``positions`` [batch] int64, device tensors) and return
+        the next-token logits [batch, vocab] and / or their arg-max [batch] int32.  Positions must arrive in order from 0."""
+        h = self._ensure_packed()
+        dev = self._device()
+        ids = _as(token_ids, torch.int64, dev, "token_ids").reshape(-1)
+        pos = _as(positions, torch.int64, dev, "positions").reshape(-1)
+        if ids.numel() != cache.batch or pos.numel() != cache.batch:
+            raise ValueError(f"token_ids / positions: expected {cache.batch} entries")
+        if logits_out is None and want_logits:
+            logits_out = torch.empty((cache.batch, cache.vocab), dtype=torch.float32, device=dev)
+        if next_out is None and want_next:
+            next_out = torch.empty((cache.batch,), dtype=torch.int32, device=dev)
+        if logits_out is None and next_out is None:
+            raise ValueError("decode_step: ask for logits, the arg-max, or both")
+        with torch.cuda.device(dev):
+            L.check(L.load().caco_model_decode_step(h, L.ptr(cache.view), L.ptr(ids), L.ptr(pos), cache.batch, cache.seq,
+                                                    cache.capacity, L.ptr(logits_out), L.ptr(next_out), L.stream_ptr()),
+                    "caco_model_decode_step")
+        if logits_out is not None and next_out is not None:
+            return logits_out, next_out
+        return logits_out if logits_out is not None else next_out
+
     def forward(self, audio_patches, audio_time_inds, audio_freq_inds, audio_mask, text_input_ids, text_mask,
                 deterministic: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """caco.py:242-261."""
@@ -536,6 +599,15 @@ class CACO(nn.Module):
         for x in (ids, mk, t):
             x.record_stream(cur)
         return a, t
+
+
+class DecodeCache:
+    """Key / value cache of one incremental captioning decode (``CACO.decode_begin``): a caller-owned device buffer laid out by
+    the library (caco_model_decode_cache_bytes), plus the shape it was made for."""
+
+    def __init__(self, storage: torch.Tensor, view: torch.Tensor, batch: int, seq: int, capacity: int, vocab: int):
+        self.storage, self.view = storage, view          # view: the 256-byte aligned window the library uses
+        self.batch, self.seq, self.capacity, self.vocab = batch, seq, capacity, vocab
 
 
 def _as(t: torch.Tensor, dtype, dev, name: str) -> torch.Tensor:

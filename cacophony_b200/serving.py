@@ -10,11 +10,11 @@ issued on the same stream (or otherwise ordered), as any two calls on one model 
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
-from .model import CACO
+from .model import CACO, DecodeCache
 
 
 class GraphedPairs:
@@ -68,3 +68,58 @@ class GraphedPairs:
         self.mask.copy_(text_mask, non_blocking=True)
         self.graph.replay()
         return self.at, self.ta
+
+
+class GraphedDecodeStep:
+    """One KV-cached captioning decode step (``CACO.decode_step``: one token per sequence through 12 text layers, 4 decoder layers
+    and the vocabulary projection, ~140 launches) as one CUDA graph for a fixed (batch, audio tokens, capacity).  Token ids and
+    positions are read from static device buffers, so the same graph serves every step of every request; ``begin`` resets the
+    (static) cache for a new batch of clips outside the graph.  Same re-capture rule as ``GraphedPairs``."""
+
+    def __init__(self, model: CACO, batch: int, seq: int, capacity: int, warmup: int = 2):
+        dev = model._device()
+        if dev.type != "cuda":
+            raise RuntimeError("cacophony_b200 runs on a CUDA device only (no CPU fallback)")
+        self.model, self.batch, self.seq, self.capacity = model, batch, seq, capacity
+        D = model.audio_config.hidden_size
+        self.ids = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.cache: DecodeCache = model.decode_begin(torch.zeros((batch, seq, D), dtype=torch.float32, device=dev),
+                                                     torch.ones((batch, seq), dtype=torch.float32, device=dev), capacity)
+        self.logits = torch.empty((batch, self.cache.vocab), dtype=torch.float32, device=dev)
+        self.next = torch.empty(batch, dtype=torch.int32, device=dev)
+        self._warmup = max(1, warmup)
+        self._capture()
+
+    def _run(self) -> None:
+        self.model.decode_step(self.cache, self.ids, self.pos, logits_out=self.logits, next_out=self.next)
+
+    def _capture(self) -> None:
+        dev = self.model._device()
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up off the capture: workspace, function attributes
+            for _ in range(self._warmup):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(self.graph):
+            self._run()
+        self._generation = self.model.generation()
+        self.recaptures = getattr(self, "recaptures", -1) + 1
+
+    @torch.no_grad()
+    def begin(self, audio_hidden_state: torch.Tensor, audio_mask: torch.Tensor) -> None:
+        """New batch of clips: empty the cache, store their cross-attention keys / values (eager, once per request)."""
+        self.model.decode_begin(audio_hidden_state, audio_mask, self.capacity, cache=self.cache)
+
+    @torch.no_grad()
+    def step(self, token_ids: torch.Tensor, positions: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(next-token logits [batch, vocab], their arg-max [batch] int32) — views of static buffers, valid until the next step."""
+        if self.model._packed_key is None or self.model.generation() != self._generation:
+            self._capture()                                 # the handle released memory the old graph points into
+        self.ids.copy_(token_ids.reshape(-1), non_blocking=True)
+        self.pos.copy_(positions.reshape(-1), non_blocking=True)
+        self.graph.replay()
+        return self.logits, self.next

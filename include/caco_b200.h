@@ -15,6 +15,7 @@
 #ifndef CACO_B200_H_
 #define CACO_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -221,6 +222,22 @@ int caco_model_text_embedding(caco_model* m, const int64_t* ids, const float* ma
 int caco_model_decoder_logits(caco_model* m, const float* text_hidden, const float* text_mask, const float* audio_hidden,
                               const float* audio_mask, int batch, int T, int S, float* logits_out, void* stream);
 int caco_model_decoder_vocab(const caco_model* m);
+/* KV-cached captioning decode ("KV-cached sampling").  The reference's loop (eval_caco_torch.py:411-472)
+ * re-runs CACO.get_decoder_logits on the whole prefix for every token; text tower and decoder are causal, so a step here pushes
+ * ONE new token per sequence through them against cached keys / values (what the JAX twin does, caco/caco.py:154-230) — the same
+ * next-token logits as the full-prefix call.
+ *   cache     caller-owned DEVICE buffer of caco_model_decode_cache_bytes(m, batch, S, capacity) bytes, 256-byte aligned;
+ *             capacity = the longest sequence (prompt + generated tokens) it can hold, <= max_pos
+ *   begin     empties the cache and stores the cross-attention keys / values of audio_hidden [batch, S, hidden] f32 (the audio
+ *             tower's hidden_out) and a copy of audio_mask [batch, S] f32
+ *   step      ids [batch] int64 = each sequence's newest token, positions [batch] int64 = its index in the sequence (DEVICE
+ *             arrays, so a step can be captured in a CUDA graph and replayed); logits_out [batch, vocab] f32 and / or next_out
+ *             [batch] int32 = arg-max of the logits (either may be NULL).  Steps must be issued in position order from 0. */
+size_t caco_model_decode_cache_bytes(const caco_model* m, int batch, int S, int capacity);
+int caco_model_decode_begin(caco_model* m, void* cache, size_t cache_bytes, const float* audio_hidden, const float* audio_mask,
+                            int batch, int S, int capacity, void* stream);
+int caco_model_decode_step(caco_model* m, void* cache, const int64_t* ids, const int64_t* positions, int batch, int S,
+                           int capacity, float* logits_out, int* next_out, void* stream);
 /* cross-attention core used by it: q [batch*Tq, heads*64] f16 (row pitch ldq), kv [batch*Skv, 2*heads*64] f16 (k | v),
  * key_mask [batch, Skv] f32, out [batch*Tq, heads*64] f16 (roberta.py:76-102 with key_value_states). */
 int caco_attention_cross(const void* q, int ldq, const void* kv, const float* key_mask, void* out, int batch, int Tq, int Skv,

@@ -1,5 +1,6 @@
-"""Captioning (row f-4): greedy decode throughput — audio tower once, then one get_decoder_logits call (text tower + 4 decoder
-layers + 50 265-way projection on the whole prefix) per generated token, as the reference's decode loop does."""
+"""Captioning (row f-4): greedy decode throughput — audio tower once, then per generated token either one get_decoder_logits call
+on the whole prefix (text tower + 4 decoder layers + 50 265-way projection, as the reference's decode loop does: "full_prefix"),
+or one KV-cached step on the newest token ("kv_cache"), eager or replayed from a CUDA graph ("kv_cache_graph")."""
 import json
 import sys
 import time
@@ -12,14 +13,19 @@ from cacophony_b200 import eval as ev
 
 torch.manual_seed(0)
 model = cb.create_caco_model().cuda()
+ARMS = {"full_prefix": dict(use_cache=False), "kv_cache": dict(use_cache=True), "kv_cache_graph": dict(use_cache=True, use_graph=True)}
 for B, steps in ((1, 32), (8, 32), (64, 32)):
     w = (0.1 * (2 * torch.rand(B, 160000, device="cuda") - 1)).float()
     ab = cb.prepare_audio_batch(w, cb.DatasetConfig(patches_seq_len=500), "cuda")
-    ev.decode_caption_ids(model, ab, eos_id=-1, max_decode_length=4)          # warm-up (eos never hit: fixed length)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = ev.decode_caption_ids(model, ab, eos_id=-1, max_decode_length=steps)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(json.dumps({"batch": B, "generated_tokens_per_clip": steps, "s": round(dt, 4), "tokens_per_s": round(B * steps / dt, 1),
-                      "ms_per_step": round(1e3 * dt / steps, 3), "shape": list(out.shape)}), flush=True)
+    outs = {}
+    for arm, kw in ARMS.items():
+        ev.decode_caption_ids(model, ab, eos_id=-1, max_decode_length=4, **kw)          # warm-up (eos never hit: fixed length)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ev.decode_caption_ids(model, ab, eos_id=-1, max_decode_length=steps, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        outs[arm] = out
+        print(json.dumps({"arm": arm, "batch": B, "generated_tokens_per_clip": steps, "s": round(dt, 4),
+                          "tokens_per_s": round(B * steps / dt, 1), "ms_per_step": round(1e3 * dt / steps, 3),
+                          "same_tokens_as_full_prefix": bool(torch.equal(out, outs["full_prefix"]))}), flush=True)

@@ -107,6 +107,10 @@ def test_no_cpu_fallback():
     headless = cb.CACO(a_cfg, cb.RobertaConfig(vocab_size=10, num_hidden_layers=1), cb.CACOConfig())
     with pytest.raises(ValueError, match="Decoder module not initialized"):
         headless.get_decoder_logits(None, None, None, None)
+    with pytest.raises(ValueError, match="Decoder module not initialized"):
+        headless.decode_begin(torch.zeros(1, 8, 768), torch.ones(1, 8), capacity=4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.decode_begin(torch.zeros(1, 8, 768), torch.ones(1, 8), capacity=4)
     with pytest.raises(RuntimeError, match="CUDA"):
         m.get_decoder_logits(torch.zeros(1, 8, 768), torch.ones(1, 8), torch.zeros(1, 4, dtype=torch.long), torch.ones(1, 4))
 

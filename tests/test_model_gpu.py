@@ -242,6 +242,73 @@ def test_decoder_logits_and_greedy_decode(golden_dir, synthetic_state_dict):
         gen = torch.cat([gen, nxt[:, None]], dim=1)
 
 
+def test_kv_cached_decode_matches_full_prefix(synthetic_state_dict):
+    """Row f-4 ("KV-cached sampling"): text tower and decoder are causal (roberta.py:297-310, 346-355), so pushing token t alone
+    against the key / value cache must give the logits the full-prefix call get_decoder_logits(...)[:, t] gives — the call the
+    reference's loop repeats for every token (eval_caco_torch.py:411-472).  Tolerance: 1e-4 of a row's spread (measured: 0 or
+    rounding-level); greedy tokens equal; the CUDA-graph replay of a step equals the eager step bit for bit."""
+    from cacophony_b200 import eval as ev
+    from cacophony_b200 import serving
+    c = MODEL_CASES["model_s4_decoder"]
+    model = _model(c["seed"], c["sharp"], synthetic_state_dict, False, c["decoder_layers"])
+    waves, ids, _ = case_inputs(c)
+    ab = _audio_batch(waves, c["max_patches"])
+    ids_t = torch.from_numpy(ids).cuda()
+    B, T = ids_t.shape
+    _, a_hid = model.get_audio_embedding(**ab)
+    full = model.get_decoder_logits(a_hid, ab["audio_mask"], ids_t, torch.ones((B, T), device="cuda"))
+    cache = model.decode_begin(a_hid, ab["audio_mask"], capacity=T)
+    stepper = serving.GraphedDecodeStep(model, B, a_hid.shape[1], T)
+    stepper.begin(a_hid, ab["audio_mask"])
+    worst = 0.0
+    for t in range(T):
+        pos = torch.full((B,), t, dtype=torch.long, device="cuda")
+        lg, nx = model.decode_step(cache, ids_t[:, t], pos, want_logits=True, want_next=True)
+        ref = full[:, t]
+        spread = (ref - ref.mean(-1, keepdim=True)).norm(dim=-1)
+        worst = max(worst, float(((lg - ref).norm(dim=-1) / spread).max()))
+        assert torch.equal(nx.long(), lg.argmax(-1))            # device arg-max of the same logits (no ties in random logits)
+        g_lg, g_nx = stepper.step(ids_t[:, t], pos)
+        assert torch.equal(g_lg, lg) and torch.equal(g_nx, nx), f"graph replay differs from the eager step at position {t}"
+    print("kv-cached decode: worst row error / row spread vs the full-prefix logits", worst)
+    assert worst < 1e-4
+    # the whole loop: cached == cached + graph, and == the reference-style loop unless a top-2 near-tie flips
+    kw = dict(bos_id=0, eos_id=2, max_decode_length=8, temperature=0.0)
+    out_full = ev.decode_caption_ids(model, ab, use_cache=False, **kw)
+    out_kv = ev.decode_caption_ids(model, ab, use_cache=True, **kw)
+    out_g = ev.decode_caption_ids(model, ab, use_cache=True, use_graph=True, **kw)
+    assert torch.equal(out_kv, out_g)
+    if not (out_kv.shape == out_full.shape and torch.equal(out_kv, out_full)):
+        # only a top-2 near-tie may flip a token: check the first differing step on the full-prefix logits
+        n = min(out_kv.shape[1], out_full.shape[1])
+        step = int((out_kv[:, :n] != out_full[:, :n]).any(0).nonzero()[0])
+        lg = model.get_decoder_logits(a_hid, ab["audio_mask"], out_full[:, :step], torch.ones((B, step), device="cuda"))[:, -1]
+        top2 = lg.sort(-1).values[:, -2:]
+        rows = (out_kv[:, step] != out_full[:, step])
+        assert float((top2[rows, 1] - top2[rows, 0]).max()) < 1e-3, "cached decode diverged from the full-prefix loop"
+    # temperature sampling draws from the same distribution (same logits, same generator state -> same tokens)
+    g1, g2 = torch.Generator(device="cuda").manual_seed(3), torch.Generator(device="cuda").manual_seed(3)
+    kw = dict(bos_id=0, eos_id=2, max_decode_length=5, temperature=0.7)
+    s_full = ev.decode_caption_ids(model, ab, use_cache=False, generator=g1, **kw)
+    s_kv = ev.decode_caption_ids(model, ab, use_cache=True, generator=g2, **kw)
+    assert s_kv.shape[0] == B and s_kv.shape[1] <= 6 and int(s_kv[0, 0]) == 0
+    print("kv-cached sampling equals full-prefix sampling:", bool(s_full.shape == s_kv.shape and torch.equal(s_full, s_kv)))
+    # batch 1, a cache reused for a second request, error behaviour
+    c1 = model.decode_begin(a_hid[1:2], ab["audio_mask"][1:2], capacity=T)
+    l1 = model.decode_step(c1, ids_t[1:2, 0], torch.zeros(1, dtype=torch.long, device="cuda"))
+    model.decode_begin(a_hid[0:1], ab["audio_mask"][0:1], capacity=T, cache=c1)
+    l0 = model.decode_step(c1, ids_t[0:1, 0], torch.zeros(1, dtype=torch.long, device="cuda"))
+    for row, lg in ((1, l1), (0, l0)):
+        ref = full[row, 0]
+        assert float((lg[0] - ref).norm() / (ref - ref.mean()).norm()) < 1e-4
+    with pytest.raises(ValueError):
+        model.decode_step(cache, ids_t[:1, 0], torch.zeros(1, dtype=torch.long, device="cuda"))
+    with pytest.raises(ValueError):
+        model.decode_begin(a_hid, ab["audio_mask"], capacity=10_000)
+    with pytest.raises(ValueError):
+        model.decode_begin(a_hid, ab["audio_mask"], capacity=T + 1, cache=cache)
+
+
 def test_encode_audio_alias_equals_two_step(synthetic_state_dict):
     c = MODEL_CASES["model_s0"]
     model = _model(c["seed"], c["sharp"], synthetic_state_dict)
