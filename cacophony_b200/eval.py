@@ -176,7 +176,7 @@ USE_KV_CACHE = False
 def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id: int = 0, eos_id: int = 2,
                        max_decode_length: int = 100, temperature: float = 0.0,
                        generator: Optional[torch.Generator] = None, use_cache: Optional[bool] = None,
-                       use_graph: bool = False) -> torch.Tensor:
+                       use_graph: Any = False) -> torch.Tensor:
     """The loop of decode_caption (eval_caco_torch.py:411-472) on token ids, for a whole batch: BOS, then one token per step
     from the decoder logits of the sequence so far (the reference's own call passes keyword names ``RobertaDecoder.forward``
     does not have — SURVEY.md 2 row 6 — so the call it means, ``CACO.get_decoder_logits``, is the one made here).
@@ -186,8 +186,8 @@ def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id
     use_cache (default ``USE_KV_CACHE``): False re-runs ``get_decoder_logits`` on the full prefix every step, as the reference
     does; True pushes only the newest token through text tower and decoder against cached keys / values
     (``CACO.decode_begin`` / ``decode_step``) — both towers are causal, so the logits are the same.
-    use_graph (with the cache): replay each step from one CUDA graph (``serving.GraphedDecodeStep``) — a step is ~140 small
-    launches, launch-bound at small batches."""
+    use_graph (with the cache): replay each step from one CUDA graph — a step is ~140 small launches, launch-bound at small
+    batches.  True captures a ``serving.GraphedDecodeStep`` for this call; pass an instance to reuse one across requests."""
     _, audio_hidden = model.get_audio_embedding(audio_patches=audio_batch["audio_patches"],
                                                 audio_time_inds=audio_batch["audio_time_inds"],
                                                 audio_freq_inds=audio_batch["audio_freq_inds"],
@@ -204,7 +204,12 @@ def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id
         capacity = max(1, min(int(max_decode_length), model.text_config.max_position_embeddings))
         if use_graph:
             from .serving import GraphedDecodeStep
-            stepper = GraphedDecodeStep(model, B, int(audio_hidden.shape[1]), capacity)
+            if isinstance(use_graph, GraphedDecodeStep):          # a captured step kept across requests of one shape
+                stepper = use_graph
+                if (stepper.batch, stepper.seq) != (B, int(audio_hidden.shape[1])) or stepper.capacity < capacity:
+                    raise ValueError("use_graph: the captured step was made for another batch / audio length / capacity")
+            else:
+                stepper = GraphedDecodeStep(model, B, int(audio_hidden.shape[1]), capacity)
             stepper.begin(audio_hidden, audio_batch["audio_mask"])
         else:
             cache = model.decode_begin(audio_hidden, audio_batch["audio_mask"], capacity)
