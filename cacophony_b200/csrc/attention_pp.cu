@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "caco_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -108,7 +110,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
   const int D = a.H * DH, nb = a.n_blocks;
   const int n_local = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = n_local * nb;
-  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 4)) ? g_attn_trace : nullptr;
+  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 4 || warp == 8)) ? g_attn_trace : nullptr;
 
   if (tid == 0) {
     if ((sb & 1023u) != 0) __trap();
@@ -190,15 +192,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
           }
         }
         // additive key bias (0 = live key, -inf = masked key or padding past S) + per-block "any masked" flag
-        for (int j0 = 0; j0 < a.max_keys; j0 += BN) {
-          bool any = false;
-          for (int j = j0 + lane; j < j0 + BN; j += 32) {
+        for (int j0 = 0, blk = 0; j0 < a.max_keys; j0 += BN, ++blk) {
+          int chunks = 0;                                      // bit c: the block's 32-key chunk c has a masked key
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int j = j0 + c * 32 + lane;
             const bool live = (j < a.S) && (__ldg(a.mask + (size_t)b * a.S + j) != 0.0f);
             s_bias[ib * a.max_keys + j] = live ? 0.0f : -INFINITY;
-            any |= !live;
+            if (__any_sync(0xffffffffu, !live)) chunks |= 1 << c;
           }
-          any = __any_sync(0xffffffffu, any);
-          if (lane == 0) s_flag[ib * 32 + j0 / BN] = any ? 1 : 0;
+          if (lane == 0) s_flag[ib * 32 + blk] = chunks;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + B_BIASFULL + 8 * ib);
@@ -212,8 +215,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
       // only if a probe came back negative.  A second issuing thread (one per tile) was measured 15 % slower.
       constexpr uint32_t idesc_qk = umma_idesc_f16(BM, BN);
       constexpr uint32_t idesc_pv = umma_idesc_f16(BM, DH, false, true);
-      auto issue_qk = [&](int g, int x) {      // S_x = Q_x K_g^T
-        const int ib = (g / nb) & 1, st = g % NST;
+      // (block g = block j of item it: the pairs are counted along with g — a runtime integer division goes through the MUFU
+      // pipe, which the softmax warps of this SM sub-partition keep saturated with exp2)
+      struct Pos { int it, j; };
+      auto next = [&](Pos p) -> Pos { return (p.j + 1 == nb) ? Pos{p.it + 1, 0} : Pos{p.it, p.j + 1}; };
+      auto issue_qk = [&](int g, Pos p, int x) {      // S_x = Q_x K_g^T
+        const int ib = p.it & 1, st = g % NST;
         const uint32_t k = sb + OFF_K + st * Q_TILE, q = sb + OFF_Q + (ib * 2 + x) * Q_TILE;
         const uint64_t k0 = umma_desc_kmajor_sw128(k), k1 = umma_desc_kmajor_sw64(k + 16384);
         const uint64_t a0 = umma_desc_kmajor_sw128(q), a1 = umma_desc_kmajor_sw64(q + 16384);
@@ -225,9 +232,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
         umma_commit<1>(bar + B_SFULL + 8 * x);
         if (x == 1) umma_commit<1>(bar + B_KEMPTY + 8 * st);
       };
-      auto issue_pv = [&](int g, int x, int ks0, int ks1) {      // O_x += P_x V_g, k-steps [ks0, ks1): A = P_x from tensor
-        const int st = g % NST;                                   // memory (packed fp16, 8 columns per 16 keys), B = V_g MN-major
-        const uint32_t acc0 = (g % nb) ? 1u : 0u;
+      auto issue_pv = [&](int g, Pos p, int x, int ks0, int ks1) {   // O_x += P_x V_g, k-steps [ks0, ks1): A = P_x from tensor
+        const int st = g % NST;                                       // memory (packed fp16, 8 columns per 16 keys), B = V_g MN-major
+        const uint32_t acc0 = p.j ? 1u : 0u;
 #pragma unroll
         for (int ks = ks0; ks < ks1; ++ks) {
           const uint64_t vb = umma_desc_mnmajor_sw128(sb + OFF_V + st * 32768 + ks * 2048, 16384);
@@ -236,54 +243,61 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
         }
       };
       // barriers of Q K^T(g): Q (first block of an item) and K
-      auto probe_qk_inputs = [&](int g) -> bool {
+      auto probe_qk_inputs = [&](int g, Pos p) -> bool {
         bool ok = mbar_test(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1);
-        if (g % nb == 0) ok = mbar_test(bar + B_QFULL + 8 * ((g / nb) & 1), ((g / nb) >> 1) & 1) && ok;
+        if (p.j == 0) ok = mbar_test(bar + B_QFULL + 8 * (p.it & 1), (p.it >> 1) & 1) && ok;
         return ok;
       };
-      auto wait_qk_inputs = [&](int g) {
-        const int it = g / nb;
-        if (g % nb == 0) mbar_wait(bar + B_QFULL + 8 * (it & 1), (it >> 1) & 1);
+      auto wait_qk_inputs = [&](int g, Pos p) {
+        if (p.j == 0) mbar_wait(bar + B_QFULL + 8 * (p.it & 1), (p.it >> 1) & 1);
         mbar_wait(bar + B_KFULL + 8 * (g % NST), (g / NST) & 1);
       };
       bool ok_v = false, ok_qk = false, ok_pa = false, ok_pb = false;
+      Pos p0{0, 0};
       if (total > 0) {
-        wait_qk_inputs(0);
+        wait_qk_inputs(0, p0);
         tc_fence_after();
-        issue_qk(0, 0);
-        issue_qk(0, 1);
+        issue_qk(0, p0, 0);
+        issue_qk(0, p0, 1);
       }
       for (int g = 0; g < total; ++g) {
         PP_STAMP(0, g, 0);
+        if (trace != nullptr && (g == 0 || g == 63)) {         // wall-clock anchors: SM clock = cycles / ns between them
+          unsigned long long ns;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+          trace[(0 * 64 + g) * 8 + 5] = (long long)ns;
+        }
         const int st = g % NST;
         const bool more = g + 1 < total;
+        const Pos p1 = next(p0), p2 = next(p1);
         if (!ok_v) mbar_wait(bar + B_VFULL + 8 * st, (g / NST) & 1);
-        if (more && !ok_qk) wait_qk_inputs(g + 1);
+        if (more && !ok_qk) wait_qk_inputs(g + 1, p1);
         if (!ok_pa) mbar_wait(bar + B_PFULL + 8 * 0, g & 1);
         PP_STAMP(0, g, 1);
         tc_fence_after();
         // ---- tile A
-        issue_pv(g, 0, 0, 4);
+        issue_pv(g, p0, 0, 0, 4);
         ok_pb = mbar_test(bar + B_PFULL + 8 * 1, g & 1);                   // tile B's P of this block
-        issue_pv(g, 0, 4, 8);
+        issue_pv(g, p0, 0, 4, 8);
         umma_commit<1>(bar + B_PVDONE + 8 * 0);
-        if (more) issue_qk(g + 1, 0);                  // overwrites S_A / P_A: ordered after P_A V by the in-order pipe
+        if (more) issue_qk(g + 1, p1, 0);              // overwrites S_A / P_A: ordered after P_A V by the in-order pipe
         PP_STAMP(0, g, 2);
         if (!ok_pb) mbar_wait(bar + B_PFULL + 8 * 1, g & 1);
         PP_STAMP(0, g, 3);
         tc_fence_after();
         // ---- tile B, with the probes for block g + 1 between its MMAs
-        issue_pv(g, 1, 0, 4);
+        issue_pv(g, p0, 1, 0, 4);
         ok_v = more && mbar_test(bar + B_VFULL + 8 * ((g + 1) % NST), ((g + 1) / NST) & 1);
-        ok_qk = (g + 2 < total) && probe_qk_inputs(g + 2);
-        issue_pv(g, 1, 4, 8);
+        ok_qk = (g + 2 < total) && probe_qk_inputs(g + 2, p2);
+        issue_pv(g, p0, 1, 4, 8);
         umma_commit<1>(bar + B_PVDONE + 8 * 1);
         umma_commit<1>(bar + B_VEMPTY + 8 * st);
         if (more) {
-          issue_qk(g + 1, 1);
+          issue_qk(g + 1, p1, 1);
           ok_pa = mbar_test(bar + B_PFULL + 8 * 0, (g + 1) & 1);            // tile A's P of the next block
         }
         PP_STAMP(0, g, 4);
+        p0 = p1;
       }
     }
   } else {
@@ -297,147 +311,226 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
     const uint32_t b_sfull = bar + B_SFULL + 8 * x, b_pfull = bar + B_PFULL + 8 * x, b_pvdone = bar + B_PVDONE + 8 * x;
     float m_ref = -INFINITY, l_run = 0.f;
     int b = 0, h = 0, q0 = 0;
+    // Item epilogue, deferred (measured on the CTA-0 timeline: done right after an item's last block it kept the tile's warps
+    // away from the next item's first S for ~3300 cycles — waiting for the last P V, 1600 cycles of O -> fp16 -> smem -> TMA
+    // store — while the issuing thread idled; an item is only 4 blocks of ~3200).  Now the finished item's O_x stays in tensor
+    // memory while the warps run the NEXT item's first block; its P V may not be issued before O_x has been read (it
+    // overwrites O_x), so the rows are read into registers just before that block's P is published, and scaling, conversion and
+    // the TMA store happen after the publish, under the issuing thread's MMAs.
+    bool pend = false;                 // a finished item of this tile still has its O_x in tensor memory
+    float pend_l = 0.f;
+    int pend_ib = 0, pend_b = 0, pend_h = 0, pend_q0 = 0, pend_par = 0;
+    auto drain_o = [&](uint32_t (&o)[6][16], int par) {       // O_x rows -> registers, once the item's last P V has retired
+      mbar_wait(b_pvdone, par);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 6; ++c) tmem_ld_32x16(t_o + c * 16, o[c]);
+      tmem_ld_wait();
+    };
+    auto store_item = [&](const uint32_t (&o)[6][16], float l, int ib, int bb, int hh, int qq0) {
+      const float inv = 1.0f / l;                              // l == 0 (no live key): NaN row, like torch.softmax
+      // O rows / l -> fp16 -> the item's (dead) Q_x buffer in the swizzled layouts of the two output tensor maps -> one TMA
+      // store per warp (32 rows x 64 + 32 columns); rows past the clip's end are clipped by the hardware
+      uint8_t* stage = smem + OFF_Q + (ib * 2 + x) * Q_TILE;
+      uint8_t* r0 = stage + row * 128;
+      uint8_t* r1 = stage + 16384 + row * 64;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __half2 hf = __floats2half2_rn(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
+          pk[i] = *reinterpret_cast<uint32_t*>(&hf);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int ch = c * 2 + k;                            // 16-byte chunk (8 fp16) 0..11 of the 96-column row
+          const uint4 u = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          if (ch < 8) *reinterpret_cast<uint4*>(r0 + ((ch ^ (row & 7)) << 4)) = u;                       // SWIZZLE_128B
+          else *reinterpret_cast<uint4*>(r1 + (((ch - 8) ^ ((row >> 1) & 3)) << 4)) = u;                 // SWIZZLE_64B
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int qrow = qq0 + x * BM + quarter * 32;
+        tma_store_3d(&map_o64, sb + OFF_Q + (ib * 2 + x) * Q_TILE + quarter * 32 * 128, hh * DH, qrow, bb);
+        tma_store_3d(&map_o32, sb + OFF_Q + (ib * 2 + x) * Q_TILE + 16384 + quarter * 32 * 64, hh * DH + 64, qrow, bb);
+        tma_store_commit();
+      }
+      __syncwarp();
+    };
+    // the store's read of the staging buffer is not waited for in line (~1000 cycles on the timeline): the issuing lane checks
+    // it one block later, when it has long completed, and only then hands the buffer back to the Q producer
+    int store_ib = -1;
+    auto finish_store = [&]() {
+      if (store_ib >= 0) {
+        if (lane == 0) {
+          tma_store_wait_read<0>();                            // smem may be refilled with the next-but-one item's Q
+          mbar_arrive(bar + B_ITEMDONE + 8 * store_ib);
+        }
+        __syncwarp();
+        store_ib = -1;
+      }
+    };
+    int it = 0, j = 0;                 // item and block within it (counted, not divided: integer division runs on the MUFU pipe
+                                       // the other tile's exp2 pass is saturating)
     for (int g = 0; g < total; ++g) {
-      const int it = g / nb, j = g - it * nb, ib = it & 1;
+      const int ib = it & 1;
       if (j == 0) {
         decode(it, b, h, q0);
         mbar_wait(bar + B_BIASFULL + 8 * ib, (it >> 1) & 1);
         m_ref = -INFINITY;
         l_run = 0.f;
       }
-      const bool masked = s_flag[ib * 32 + j] != 0;           // warp-uniform
+      const int mchunks = s_flag[ib * 32 + j];                // warp-uniform: which 32-key chunks of the block have masked keys
+      const bool masked = mchunks != 0;
       const float* bias = s_bias + ib * a.max_keys + j * BN;
-      PP_STAMP(1, g, 0);
+      PP_STAMP(1 + x, g, 0);
       mbar_wait(b_sfull, g & 1);                              // S_x(g) complete => every earlier MMA (incl. P_x V of g-1) retired
-      PP_STAMP(1, g, 1);
+      PP_STAMP(1 + x, g, 1);
       tc_fence_after();
-      // ---- the whole row of scores, once: four loads in flight together
-      uint32_t s[BN];
+      // The block's softmax, instantiated separately for blocks with and without masked keys (only a clip's last block has any):
+      // with one body and an in-place "s += bias" on the masked path the two paths' register assignments of s[] had to be
+      // merged, which cost the common unmasked path 128 register moves per block.  Leaves P_x stored (not yet published).
+      auto softmax_block = [&](auto masked_c) {
+        constexpr bool MASKED = decltype(masked_c)::value;
+        // ---- the whole row of scores, once: four loads in flight together
+        uint32_t s[BN];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-      tmem_ld_wait();
-      PP_STAMP(1, g, 2);
-      // ---- row maximum of the raw scores (scale > 0, so max commutes with the scaling); masked blocks add the key bias first
-      float mx = -INFINITY;
-      if (masked) {
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        tmem_ld_wait();
+        PP_STAMP(1 + x, g, 2);
+        // ---- row maximum of the raw scores (scale > 0, so max commutes with the scaling).  Eight independent FMNMX3 chains: one chain of 64 dependent maxima was ~375 cycles of pure ALU latency on
+        // the tile's critical path; the maximum is exact, so the grouping does not change the result.
+        if (MASKED) {                                           // key bias (0 / -inf) onto the chunks that have masked keys
 #pragma unroll
-        for (int i = 0; i < BN / 2; ++i) {
-          const uint64_t sb2 = add_f32x2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])),
-                                         *reinterpret_cast<const uint64_t*>(bias + 2 * i));
-          float s0, s1;
-          unpack_f32x2(sb2, s0, s1);
-          s[2 * i] = __float_as_uint(s0);
-          s[2 * i + 1] = __float_as_uint(s1);
-          mx = max3(mx, s0, s1);
+          for (int c = 0; c < NCH; ++c)
+            if ((mchunks >> c) & 1) {
+#pragma unroll
+              for (int i = c * 16; i < c * 16 + 16; ++i) {
+                float s0, s1;
+                unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])),
+                                       *reinterpret_cast<const uint64_t*>(bias + 2 * i)), s0, s1);
+                s[2 * i] = __float_as_uint(s0);
+                s[2 * i + 1] = __float_as_uint(s1);
+              }
+            }
         }
-      } else {
+        float mx8[8];
 #pragma unroll
-        for (int i = 0; i < BN / 2; ++i) mx = max3(mx, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-      }
-      mx *= a.scale_log2;                                     // -inf stays -inf
-      // ---- lazy rescale of O_x and l (only when the maximum grew by more than 2^8 since the reference was taken)
-      const bool need = mx > m_ref + RESCALE_T;               // m_ref == -inf: true iff this block has a live key
-      if (__any_sync(0xffffffffu, need)) {
-        const float factor = need ? exp2f(m_ref - mx) : 1.0f;
-        if (j > 0) {
+        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            uint32_t o[3][16];
+        for (int i = 8; i < BN / 2; ++i) mx8[i & 7] = max3(mx8[i & 7], __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+        float mx = fmaxf(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], mx8[5]));
+        mx = max3(mx, mx8[6], mx8[7]);
+        mx *= a.scale_log2;                                     // -inf stays -inf
+        // ---- lazy rescale of O_x and l (only when the maximum grew by more than 2^8 since the reference was taken)
+        const bool need = mx > m_ref + RESCALE_T;               // m_ref == -inf: true iff this block has a live key
+        if (j == 0) {                                           // first block of an item: no O_x, l == 0, the reference
+          m_ref = mx;                                           // maximum is this block's (what the general path reduces to)
+        } else if (__any_sync(0xffffffffu, need)) {
+          const float factor = need ? exp2f(m_ref - mx) : 1.0f;
+          {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) tmem_ld_32x16(t_o + (hc * 3 + c) * 16, o[c]);
-            tmem_ld_wait();
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t o[3][16];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+              for (int c = 0; c < 3; ++c) tmem_ld_32x16(t_o + (hc * 3 + c) * 16, o[c]);
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[c][i] = __float_as_uint(__uint_as_float(o[c][i]) * factor);
-              tmem_st_32x16(t_o + (hc * 3 + c) * 16, o[c]);
+              for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[c][i] = __float_as_uint(__uint_as_float(o[c][i]) * factor);
+                tmem_st_32x16(t_o + (hc * 3 + c) * 16, o[c]);
+              }
             }
           }
+          l_run *= factor;
+          if (need) m_ref = mx;
         }
-        l_run *= factor;
-        if (need) m_ref = mx;
-      }
-      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-      PP_STAMP(1, g, 3);
-      // ---- p = exp2(s*scale - m) per PAIR of scores: one FFMA2, two MUFU.EX2, one FADD2 (two running sums), one F2FP; a chunk
-      // of 32 keys is written as packed fp16 over S columns 16c..16c+15 and published as soon as the NEXT chunk's exponentials
-      // are done (its tensor-memory store has then long completed, so the wait is free)
-      uint64_t sum2 = pack_f32x2(0.f, 0.f);
-      const uint64_t scale2 = pack_f32x2(a.scale_log2, a.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+        PP_STAMP(1 + x, g, 3);
+        // ---- p = exp2(s*scale - m) per PAIR of scores: one FFMA2, two MUFU.EX2, one FADD2 (two running sums), one F2FP; a chunk
+        // of 32 keys is written as packed fp16 over S columns 16c..16c+15
+        // In program order a pair's FADD2 / F2FP followed its two MUFU.EX2 at a distance of one pair: with one warp per
+        // sub-partition in this phase the in-order issue then stalls on the MUFU LATENCY every pair (measured 22-25 cycles per
+        // pair against 16 of MUFU throughput).  So the pass is software-pipelined by hand in groups of four pairs: the eight
+        // exponentials of group q+1 are issued before the results of group q are consumed (volatile asm keeps that order).
+        uint64_t sum2 = pack_f32x2(0.f, 0.f);
+        const uint64_t scale2 = pack_f32x2(a.scale_log2, a.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
+        auto ex2_group = [&](int q) {                          // s[8q .. 8q+7] <- exp2(s * scale - m)
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+          for (int i = 4 * q; i < 4 * q + 4; ++i) {
+            const uint64_t t2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), scale2, negm2);
+            float t0, t1, p0, p1;
+            unpack_f32x2(t2, t0, t1);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(t0));
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(t1));
+            s[2 * i] = __float_as_uint(p0);
+            s[2 * i + 1] = __float_as_uint(p1);
+          }
+        };
         uint32_t ph[16];
+        auto use_group = [&](int q) {                          // row sum and packed fp16 of group q's probabilities
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint64_t t2 = fma_f32x2(pack_f32x2(__uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1])),
-                                        scale2, negm2);
-          float t0, t1;
-          unpack_f32x2(t2, t0, t1);
-          const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
-          sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
-          __half2 hh = __floats2half2_rn(p0, p1);
-          ph[i] = *reinterpret_cast<uint32_t*>(&hh);
+          for (int i = 4 * q; i < 4 * q + 4; ++i) {
+            const float p0 = __uint_as_float(s[2 * i]), p1 = __uint_as_float(s[2 * i + 1]);
+            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2) : "l"(pack_f32x2(p0, p1)));
+            asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph[i & 15]) : "f"(p1), "f"(p0));
+          }
+        };
+        ex2_group(0);
+#pragma unroll
+        for (int q = 0; q < BN / 8; ++q) {
+          if (q + 1 < BN / 8) ex2_group(q + 1);
+          use_group(q);
+          if ((q & 3) == 3) tmem_st_32x16(t_s + (q >> 2) * 16, ph);
         }
-        tmem_st_32x16(t_s + c * 16, ph);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_pfull);
-      {
         float s0, s1;
         unpack_f32x2(sum2, s0, s1);
         l_run += s0 + s1;
-      }
-      PP_STAMP(1, g, 4);
-      if (j == nb - 1) {
-        // ---- item epilogue: O / l -> fp16 (the next item's first P V needs this warp's next P, so O_x is safe to read)
-        mbar_wait(b_pvdone, g & 1);
-        PP_STAMP(1, g, 5);
-        tc_fence_after();
-        const float inv = 1.0f / l_run;                        // l == 0 (no live key): NaN row, like torch.softmax
-        // O tile -> fp16 -> this item's (now dead) Q_x buffer in the swizzled layouts of the two output tensor maps ->
-        // one TMA store per warp (32 rows x 64 + 32 columns); rows past the clip's end are clipped by the hardware
-        uint8_t* stage = smem + OFF_Q + (ib * 2 + x) * Q_TILE;
-        uint8_t* r0 = stage + row * 128;
-        uint8_t* r1 = stage + 16384 + row * 64;
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          uint32_t o[3][16];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) tmem_ld_32x16(t_o + (hc * 3 + c) * 16, o[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __half2 hh = __floats2half2_rn(__uint_as_float(o[c][2 * i]) * inv, __uint_as_float(o[c][2 * i + 1]) * inv);
-              pk[i] = *reinterpret_cast<uint32_t*>(&hh);
-            }
-            const int col16 = (hc * 3 + c) * 2;                // index of the first of two 16-byte chunks (8 fp16 each)
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int ch = col16 + k;                        // 0..11
-              const uint4 u = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-              if (ch < 8) *reinterpret_cast<uint4*>(r0 + ((ch ^ (row & 7)) << 4)) = u;                       // SWIZZLE_128B
-              else *reinterpret_cast<uint4*>(r1 + (((ch - 8) ^ ((row >> 1) & 3)) << 4)) = u;                 // SWIZZLE_64B
-            }
-          }
-        }
+        tmem_st_wait();
+      };
+      if (masked) softmax_block(std::true_type{});
+      else softmax_block(std::false_type{});
+      if (pend) {
+        // the previous item's O_x: out of tensor memory before this block's P V (which overwrites it) can be issued
+        uint32_t o[6][16];
+        drain_o(o, pend_par);
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          const int qrow = q0 + x * BM + quarter * 32;
-          tma_store_3d(&map_o64, sb + OFF_Q + (ib * 2 + x) * Q_TILE + quarter * 32 * 128, h * DH, qrow, b);
-          tma_store_3d(&map_o32, sb + OFF_Q + (ib * 2 + x) * Q_TILE + 16384 + quarter * 32 * 64, h * DH + 64, qrow, b);
-          tma_store_commit();
-          tma_store_wait_read<0>();                            // smem may be refilled with the next-but-one item's Q
+        if (lane == 0) mbar_arrive(b_pfull);
+        PP_STAMP(1 + x, g, 4);
+        store_item(o, pend_l, pend_ib, pend_b, pend_h, pend_q0);
+        store_ib = pend_ib;
+        PP_STAMP(1 + x, g, 6);
+        pend = false;
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_pfull);
+        PP_STAMP(1 + x, g, 4);
+        finish_store();
+      }
+      if (j == nb - 1) {
+        if (g + 1 < total) {           // defer: O_x is complete once P_x V of this block retires (b_pvdone, phase g)
+          finish_store();              // (single-block items: the previous store has had this block's time)
+          pend = true;
+          pend_l = l_run; pend_ib = ib; pend_b = b; pend_h = h; pend_q0 = q0; pend_par = g & 1;
+        } else {                       // the CTA's last item
+          finish_store();
+          uint32_t o[6][16];
+          drain_o(o, g & 1);
+          PP_STAMP(1 + x, g, 5);
+          store_item(o, l_run, ib, b, h, q0);
+          store_ib = ib;
+          finish_store();
         }
-        PP_STAMP(1, g, 6);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar + B_ITEMDONE + 8 * ib);
+        j = 0;
+        ++it;
+      } else {
+        ++j;
       }
     }
   }

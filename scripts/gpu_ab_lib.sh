@@ -1,0 +1,7 @@
+#!/bin/bash
+# A/B of two library builds on one box, interleaved process by process
+mkdir -p gpurun_out
+for r in 1 2; do
+  timeout 200 python scripts/ab_lib.py scratch/libcaco_b200_old.so old 2>&1 | tail -1 | tee -a gpurun_out/ab_lib.jsonl
+  timeout 200 python scripts/ab_lib.py cacophony_b200/libcaco_b200.so new 2>&1 | tail -1 | tee -a gpurun_out/ab_lib.jsonl
+done
