@@ -15,6 +15,19 @@
 // barrier operation on the issuing thread costs more than the overlap returns), one issuing thread per tile (15 % slower),
 // an FMA-pipe exp2 polynomial for 25-50 % of the scores (slower in every kernel version: a tile's exp2 pass is one warp per
 // SM sub-partition issuing in order, so pipe times add up instead of overlapping).
+// Second pass over the timeline (tile B traced too, wall-clock anchors: 1.67 GHz cold, 1.35-1.40 GHz under sustained load):
+//   * an item's epilogue is deferred under the next item's first block (it used to keep a tile's warps away from the next S
+//     for ~3300 cycles per 4-block item): O_x stays in tensor memory, is read into registers just before that block's P is
+//     published (whose P V overwrites it), scaled / converted / stored by TMA after the publish, and the store's read of the
+//     staging buffer is checked one block later;
+//   * the row maximum runs as eight independent FMNMX3 chains (one chain of 64: ~375 cycles of latency), blocks with and
+//     without masked keys are separate instantiations (a shared body cost the common path 128 register moves per block), the
+//     key bias is applied per 32-key chunk that has a masked key, and no thread on the critical path divides by a runtime
+//     value any more (integer division goes through the MUFU pipe the exp2 passes saturate);
+//   * the exp2 pass is at its floor: scripts/micro/xu_pipe.cu measures 10.3 cycles per MUFU.EX2 for one warp per sub-partition
+//     (1320 for a row of 128; the pass with its FFMA2 / FADD2 / F2FP: 1436) — two tiles per SM sub-partition need 2640 of a
+//     block's ~3700 cycles; a tile's chain (pass 1436 + load / max / hand-offs ~700 + its MMA leg ~1050) is what remains.
+// Outputs are bit-identical to the previous form; 0.333 -> 0.316 ms per layer under sustained load (0.272 -> 0.265 cold).
 // Unchanged: Q K^T on 128-key blocks into tensor memory, P written as packed fp16 over the S columns and consumed from tensor
 // memory (tcgen05.mma with A in TMEM), V consumed MN-major from its natural layout, lazy rescaling of O (threshold 2^8), K / V
 // 2-stage TMA rings, Q and the additive key-mask bias double-buffered per work item (256 queries of one (clip, head)), per-warp
@@ -453,10 +466,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
         PP_STAMP(1 + x, g, 3);
         // ---- p = exp2(s*scale - m) per PAIR of scores: one FFMA2, two MUFU.EX2, one FADD2 (two running sums), one F2FP; a chunk
         // of 32 keys is written as packed fp16 over S columns 16c..16c+15
-        // In program order a pair's FADD2 / F2FP followed its two MUFU.EX2 at a distance of one pair: with one warp per
-        // sub-partition in this phase the in-order issue then stalls on the MUFU LATENCY every pair (measured 22-25 cycles per
-        // pair against 16 of MUFU throughput).  So the pass is software-pipelined by hand in groups of four pairs: the eight
-        // exponentials of group q+1 are issued before the results of group q are consumed (volatile asm keeps that order).
+        // The pass is software-pipelined by hand in groups of four pairs (the eight exponentials of group q+1 are issued before
+        // the results of group q are consumed; volatile asm keeps that order).  scripts/micro/xu_pipe.cu: one warp per
+        // sub-partition issues a MUFU.EX2 every ~10.3 cycles (128 of them: 1320 cycles), F2FP goes to another pipe at ~7 cycles,
+        // and the pass in exactly this form takes 1436 cycles — what the timeline shows for it here (1450-1650 when the other
+        // tile's pass overlaps), i.e. the pass is at the MUFU floor; moving a third of the pairs to an FMA-pipe polynomial makes
+        // it 1622.
         uint64_t sum2 = pack_f32x2(0.f, 0.f);
         const uint64_t scale2 = pack_f32x2(a.scale_log2, a.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
         auto ex2_group = [&](int q) {                          // s[8q .. 8q+7] <- exp2(s * scale - m)
