@@ -87,10 +87,23 @@ static void free_ws(caco_model* m, int which) {
 }
 static int ensure_ws(caco_model* m, int which, size_t bytes) {
   if (bytes <= m->ws_bytes[which]) return 0;
+  // A caller that grows its request a little every call (a decode loop re-running get_decoder_logits on a prefix that gets one
+  // token longer each step) would otherwise synchronise, free and re-allocate every step: grow the text / decoder workspaces
+  // geometrically (at most 256 MB beyond the request).  The audio workspace (gigabytes at bench size) is sized exactly.
+  size_t want = bytes;
+  if (which != 0 && m->ws_bytes[which] > 0) {
+    const size_t geo = m->ws_bytes[which] * 2, cap = bytes + ((size_t)256 << 20);
+    if (geo > want) want = geo < cap ? geo : cap;
+  }
   free_ws(m, which);
-  cudaError_t e = cudaMalloc(&m->ws[which], bytes);
+  cudaError_t e = cudaMalloc(&m->ws[which], want);
+  if (e != cudaSuccess && want > bytes) {
+    (void)cudaGetLastError();          // clear the failed attempt: the launch wrappers report cudaGetLastError()
+    want = bytes;
+    e = cudaMalloc(&m->ws[which], want);
+  }
   if (e != cudaSuccess) return (int)e;
-  m->ws_bytes[which] = bytes;
+  m->ws_bytes[which] = want;
   return 0;
 }
 // every entry point: the handle must be used on the device it was packed on (its arenas and workspaces live there)

@@ -217,6 +217,8 @@ def decode_caption_ids(model: CACO, audio_batch: Dict[str, torch.Tensor], bos_id
         pos = torch.zeros(B, dtype=torch.long, device=dev)
     for step in range(max_decode_length):
         if use_cache:
+            if step >= capacity:                  # the full-prefix call fails at the same length (get_text_embedding)
+                raise ValueError(f"text sequence length must be <= {model.text_config.max_position_embeddings}")
             tok = generated[:, -1].contiguous()
             if stepper is not None:
                 last, greedy = stepper.step(tok, pos)

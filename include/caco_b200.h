@@ -232,7 +232,8 @@ int caco_model_decoder_vocab(const caco_model* m);
  *             tower's hidden_out) and a copy of audio_mask [batch, S] f32
  *   step      ids [batch] int64 = each sequence's newest token, positions [batch] int64 = its index in the sequence (DEVICE
  *             arrays, so a step can be captured in a CUDA graph and replayed); logits_out [batch, vocab] f32 and / or next_out
- *             [batch] int32 = arg-max of the logits (either may be NULL).  Steps must be issued in position order from 0. */
+ *             [batch] int32 = arg-max of the logits (either may be NULL).  Steps must be issued in position order from 0; a
+ *             token whose position is outside [0, capacity) is not cached (nothing is written out of bounds). */
 size_t caco_model_decode_cache_bytes(const caco_model* m, int batch, int S, int capacity);
 int caco_model_decode_begin(caco_model* m, void* cache, size_t cache_bytes, const float* audio_hidden, const float* audio_mask,
                             int batch, int S, int capacity, void* stream);
