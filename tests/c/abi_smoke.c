@@ -23,6 +23,9 @@ int main(void) {
   if (caco_frontend(NULL, 1, 16000, 100, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == 0) return 1;
   if (caco_topk_rows(NULL, 1, 1, 1, 1, NULL, NULL, NULL) == 0) return 1;
   if (caco_model_audio_embedding(NULL, NULL, NULL, NULL, NULL, 1, 1, 0, NULL, NULL, NULL) == 0) return 1;
+  if (caco_model_decode_cache_bytes(NULL, 1, 500, 32) != 0) return 1;
+  if (caco_model_decode_begin(NULL, NULL, 0, NULL, NULL, 1, 500, 32, NULL) == 0) return 1;
+  if (caco_model_decode_step(NULL, NULL, NULL, NULL, 1, 500, 32, NULL, NULL, NULL) == 0) return 1;
   printf("abi ok: version %d, %d filterbank non-zeros, launches so far %lld\n", caco_version(), nz, (long long)caco_launch_count());
   free(fb);
   return 0;
