@@ -414,8 +414,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
         for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         tmem_ld_wait();
         PP_STAMP(1 + x, g, 2);
-        // ---- row maximum of the raw scores (scale > 0, so max commutes with the scaling).  Eight independent FMNMX3 chains: one chain of 64 dependent maxima was ~375 cycles of pure ALU latency on
-        // the tile's critical path; the maximum is exact, so the grouping does not change the result.
         if (MASKED) {                                           // key bias (0 / -inf) onto the chunks that have masked keys
 #pragma unroll
           for (int c = 0; c < NCH; ++c)
@@ -430,6 +428,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap map_64, const __grid_con
               }
             }
         }
+        // ---- row maximum of the raw scores (scale > 0, so max commutes with the scaling): eight independent FMNMX3 chains (one
+        // chain of 64 dependent maxima was ~375 cycles of pure ALU latency on the tile's critical path); the maximum is exact, so
+        // the grouping does not change the result
         float mx8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
