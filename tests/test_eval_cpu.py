@@ -99,3 +99,54 @@ def test_load_caco_torch_accepts_the_reference_checkpoint_layouts():
         out = ev.load_caco_torch(None, "cpu", tokenizer="tok", state_dict=wrap(sd))
         assert set(out) == {"model", "tokenizer", "device"} and out["tokenizer"] == "tok"
         assert not out["model"].training
+
+
+class _ScriptedCaptioner:
+    """Host-logic stand-in for CACO in decode_caption_ids' cached loop: next-token logits are scripted per (sequence, position),
+    everything stays on the CPU (the arithmetic is not under test here, the loop of eval_caco_torch.py:411-472 is)."""
+
+    def __init__(self, script, vocab=11, max_pos=6):
+        self.script, self.vocab = script, vocab                       # script[b][t] = token emitted after position t
+        self.text_config = type("C", (), {"max_position_embeddings": max_pos})()
+        self.steps, self.begun = [], None
+
+    def get_audio_embedding(self, **kw):
+        B = kw["audio_patches"].shape[0]
+        return torch.zeros(B, 4), torch.zeros(B, 3, 4)
+
+    def decode_begin(self, audio_hidden, audio_mask, capacity, cache=None):
+        self.begun = (tuple(audio_hidden.shape), capacity)
+        return "cache"
+
+    def decode_step(self, cache, ids, pos, want_logits=True, want_next=False, **kw):
+        assert cache == "cache" and ids.dtype == torch.long and pos.dtype == torch.long
+        self.steps.append((ids.tolist(), pos.tolist()))
+        nxt = torch.tensor([self.script[b][int(p)] for b, p in enumerate(pos)], dtype=torch.int32)
+        if want_next and not want_logits:
+            return nxt
+        logits = torch.full((len(nxt), self.vocab), -30.0)
+        logits[torch.arange(len(nxt)), nxt.long()] = 30.0
+        return logits
+
+
+def test_cached_decode_loop_host_logic():
+    """BOS first, one token per step fed back with its position, a finished sequence keeps emitting EOS, the loop stops when every
+    sequence has finished, and the position limit raises like the full-prefix call does."""
+    ab = {"audio_patches": torch.zeros(2, 3, 256), "audio_time_inds": torch.zeros(2, 3), "audio_freq_inds": torch.zeros(2, 3),
+          "audio_mask": torch.ones(2, 3)}
+    m = _ScriptedCaptioner([[5, 2, 9, 9, 9, 9], [7, 8, 2, 9, 9, 9]])
+    out = ev.decode_caption_ids(m, ab, bos_id=0, eos_id=2, max_decode_length=5, temperature=0.0, use_cache=True)
+    assert out.tolist() == [[0, 5, 2, 2], [0, 7, 8, 2]]              # stopped after step 3: both have produced EOS
+    assert m.begun == ((2, 3, 4), 5)
+    assert m.steps == [([0, 0], [0, 0]), ([5, 7], [1, 1]), ([2, 8], [2, 2])]
+    # temperature sampling takes the logits path: with one-hot logits the sample is the scripted token
+    m = _ScriptedCaptioner([[5, 2, 9, 9, 9, 9], [7, 8, 2, 9, 9, 9]])
+    out = ev.decode_caption_ids(m, ab, bos_id=0, eos_id=2, max_decode_length=5, temperature=0.5, use_cache=True,
+                                generator=torch.Generator().manual_seed(0))
+    assert out.tolist() == [[0, 5, 2, 2], [0, 7, 8, 2]]
+    # fixed length when EOS never comes; capacity = min(max_decode_length, max positions)
+    m = _ScriptedCaptioner([[4, 4, 4, 4, 4, 4], [3, 3, 3, 3, 3, 3]])
+    out = ev.decode_caption_ids(m, ab, eos_id=2, max_decode_length=4, use_cache=True)
+    assert out.shape == (2, 5) and m.begun[1] == 4
+    with pytest.raises(ValueError, match="sequence length"):
+        ev.decode_caption_ids(m, ab, eos_id=2, max_decode_length=9, use_cache=True)      # > max_position_embeddings (6)
