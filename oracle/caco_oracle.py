@@ -331,6 +331,77 @@ def get_decoder_logits(sd, audio_hidden, audio_mask, ids, text_mask, r=None):
     return decoder_logits(sd, text_hidden, text_mask, audio_hidden, audio_mask, r=r)
 
 
+class IncrementalDecoder:
+    """The decode loop's call (eval_caco_torch.py:411-472 -> CACO.get_decoder_logits on the prefix so far) restated
+    incrementally: text tower (roberta.py:283-326) and decoder (roberta.py:337-373) are causal, so the keys / values of the
+    tokens already pushed never change — ``step`` pushes ONE token per sequence, appends its keys / values to per-layer caches
+    and returns the next-token logits ``get_decoder_logits(...)[:, t]``; the cross-attention keys / values of the audio tokens
+    are computed once (what the JAX twin caches, src/caco/caco.py:154-230).  This is the algorithm of the library's
+    caco_model_decode_begin / caco_model_decode_step; tests/test_oracle.py checks it against the full-prefix oracle."""
+
+    def __init__(self, sd, audio_hidden, audio_mask, heads: int = 12, r=None):
+        self.sd, self.heads, self.r = sd, heads, r
+        self.B, _, self.D = audio_hidden.shape
+        self.cross_bias = torch.zeros(self.B, 1, 1, audio_mask.shape[1]).masked_fill((audio_mask == 0)[:, None, None, :], float("-inf"))
+        self.t = 0
+        self.text_kv, self.dec_kv, self.cross_kv = {}, {}, {}
+        i = 0
+        while f"decoder_module.encoder.layers.{i}.intermediate.dense.weight" in sd:
+            P = f"decoder_module.encoder.layers.{i}.crossattention.self."
+            self.cross_kv[i] = (self._heads(linear(audio_hidden, sd[P + "key.weight"], sd[P + "key.bias"], r)),
+                                self._heads(linear(audio_hidden, sd[P + "value.weight"], sd[P + "value.bias"], r)))
+            i += 1
+        self.n_dec = i
+
+    def _heads(self, z):
+        return z.reshape(self.B, -1, self.heads, self.D // self.heads).transpose(1, 2)
+
+    def _attend(self, P, x, k, v, bias):
+        """RobertaAttention for one query row per sequence against given keys / values (roberta.py:86-123)."""
+        dh = self.D // self.heads
+        q = self._heads(linear(x, self.sd[P + "self.query.weight"], self.sd[P + "self.query.bias"], self.r))
+        s = _ra(q, self.r) @ _ra(k, self.r).transpose(-1, -2) / math.sqrt(dh)
+        w = torch.softmax(s if bias is None else s + bias, dim=-1)
+        o = (_ra(w, self.r) @ _ra(v, self.r)).transpose(1, 2).reshape(self.B, 1, self.D)
+        o = linear(o, self.sd[P + "output.dense.weight"], self.sd[P + "output.dense.bias"], self.r)
+        return layer_norm(o + x, self.sd[P + "output.LayerNorm.weight"], self.sd[P + "output.LayerNorm.bias"])
+
+    def _self_block(self, P, x, cache, i):
+        k = self._heads(linear(x, self.sd[P + "self.key.weight"], self.sd[P + "self.key.bias"], self.r))
+        v = self._heads(linear(x, self.sd[P + "self.value.weight"], self.sd[P + "self.value.bias"], self.r))
+        if i in cache:
+            k, v = torch.cat([cache[i][0], k], dim=2), torch.cat([cache[i][1], v], dim=2)
+        cache[i] = (k, v)
+        return self._attend(P, x, k, v, None)              # every cached key is at a position <= t: the causal mask is all-open
+
+    def _mlp(self, L, x):
+        sd, r = self.sd, self.r
+        h = torch.nn.functional.gelu(linear(x, sd[L + "intermediate.dense.weight"], sd[L + "intermediate.dense.bias"], r))
+        y = linear(h, sd[L + "output.dense.weight"], sd[L + "output.dense.bias"], r)
+        return layer_norm(y + x, sd[L + "output.LayerNorm.weight"], sd[L + "output.LayerNorm.bias"])
+
+    def step(self, ids):
+        """ids [B] int64: the token at position t of every sequence -> next-token logits [B, vocab]."""
+        sd = self.sd
+        E = "text_module.embeddings."
+        ids = ids.reshape(self.B, 1)
+        x = sd[E + "word_embeddings.weight"][ids] + sd[E + "position_embeddings.weight"][torch.full_like(ids, self.t)] \
+            + sd[E + "token_type_embeddings.weight"][torch.zeros_like(ids)]
+        x = layer_norm(x, sd[E + "LayerNorm.weight"], sd[E + "LayerNorm.bias"])
+        i = 0
+        while f"text_module.encoder.layers.{i}.attention.self.query.weight" in sd:
+            L = f"text_module.encoder.layers.{i}."
+            x = self._mlp(L, self._self_block(L + "attention.", x, self.text_kv, i))
+            i += 1
+        for i in range(self.n_dec):
+            L = f"decoder_module.encoder.layers.{i}."
+            a = self._self_block(L + "attention.", x, self.dec_kv, i)
+            c = self._attend(L + "crossattention.", a, self.cross_kv[i][0], self.cross_kv[i][1], self.cross_bias)
+            x = self._mlp(L, c)
+        self.t += 1
+        return linear(x, sd["decoder_module.decoder_proj.weight"], sd["decoder_module.decoder_proj.bias"], self.r)[:, 0]
+
+
 def contrastive_logits(sd, a_emb, t_emb):
     """caco.py:208-210: scale = exp(logit_scale); (scale·A)·Tᵀ and (scale·T)·Aᵀ."""
     s = torch.exp(sd["logit_scale"])

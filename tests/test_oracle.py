@@ -125,3 +125,29 @@ def test_decoder_logits_match_reference(golden_dir, synthetic_state_dict):
     sub = dl[:, :, ::97].numpy()
     assert np.abs(sub[valid] - g["decoder_logits_sub"][valid]).max() < 2e-4
     assert np.array_equal(dl.argmax(-1).numpy()[valid], g["decoder_argmax"][valid])
+
+
+def test_incremental_decoder_equals_full_prefix(golden_dir, synthetic_state_dict):
+    """Row f-4, "KV-cached sampling": the incremental restatement (one token per step against cached keys / values: the
+    algorithm of caco_model_decode_begin / caco_model_decode_step) gives, at every position, the logits of the full-prefix call
+    the reference's loop repeats (eval_caco_torch.py:411-472) — and therefore, on the valid positions, the golden logits the
+    reference itself produced.  fp32 re-association only: 1e-5 of the row's spread."""
+    c = MODEL_CASES["model_s4_decoder"]
+    g = np.load(os.path.join(golden_dir, "model_s4_decoder.npz"))
+    sd = synthetic_state_dict(c["seed"], c["sharp"], False, c["decoder_layers"])
+    waves, ids, mask = case_inputs(c)
+    ab = O.prepare_audio_batch(waves, c["max_patches"])
+    _, hid = O.get_audio_embedding(sd, ab["audio_patches"], ab["audio_time_inds"], ab["audio_freq_inds"], ab["audio_mask"])
+    T = 10
+    ids_t = torch.from_numpy(ids)[:, :T]
+    full = O.get_decoder_logits(sd, hid, ab["audio_mask"], ids_t, torch.ones(ids_t.shape))
+    dec = O.IncrementalDecoder(sd, hid, ab["audio_mask"])
+    for t in range(T):
+        lg = dec.step(ids_t[:, t])
+        ref = full[:, t]
+        err = (lg - ref).norm(dim=-1) / (ref - ref.mean(-1, keepdim=True)).norm(dim=-1)
+        assert float(err.max()) < 1e-5, (t, float(err.max()))
+        # where the golden caption is still valid (no padding token pushed yet) this is also the reference's own logit row
+        for b in range(2):
+            if mask[b, : t + 1].all():
+                assert np.abs(lg[b, ::97].numpy() - g["decoder_logits_sub"][b, t]).max() < 2e-4
